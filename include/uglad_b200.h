@@ -1,0 +1,104 @@
+/* uglad_b200 C-ABI: B200 (sm_100a) kernels for uGLAD's unrolled GLAD hot path.
+ *
+ * The reference (Harshs27/uGLAD) is pure Python/torch and has no FFI; each entry point
+ * below replaces the Python function cited beside it (paths under /root/reference/uglad)
+ * and is what a ctypes binding in that file would call.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to float32 unless the name ends in _host;
+ *  - matrices are dense row-major, batches are contiguous: S[b][i][j];
+ *  - eigenvector matrices are stored "vector-major": Vt[b][k][:] is eigenvector k;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *  - every function returns 0 on success, non-zero on error; uglad_last_error() gives the
+ *    message of the last failing call on the calling thread.  Nothing here falls back to
+ *    the CPU.
+ */
+#ifndef UGLAD_B200_H
+#define UGLAD_B200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UGLAD_ABI_VERSION 1
+#define UGLAD_NF 3      /* rho_l1 input features (theta_k1, S, theta_prev): glad.py:144 */
+#define UGLAD_MAX_H 8   /* largest hidden width supported by the fused MLP kernels     */
+
+typedef struct uglad_dims {
+  int B;            /* graphs held by this process                                     */
+  int D;            /* nodes per graph                                                  */
+  int L;            /* unrolled layers (glad.py:78)                                     */
+  int H;            /* hidden width of rho_l1 and lambda_f (glad_params.py:26)          */
+  int init_diag;    /* glad.py:106-117: 0 -> (S + t I)^-1, 1 -> diag(1/(S_ii + t))      */
+  int B_total;      /* graphs over all processes (mean of the Frobenius term, loss /B)  */
+  int exact_sqrt;   /* 0: reproduce torch_sqrtm.py's 10 Newton-Schulz steps; 1: sqrt    */
+  float lambda_init;/* glad.py:77                                                       */
+} uglad_dims;
+
+int uglad_abi_version(void);
+const char* uglad_last_error(void);
+
+/* number of floats in the packed parameter / gradient vector for hidden width H:
+ * [theta_init_offset | rho_l1.0.weight(H x 3) .bias(H) | rho_l1.2.weight(H x H) .bias(H) |
+ *  rho_l1.4.weight(1 x H) .bias(1) | lambda_f.0.weight(H x 2) .bias(H) |
+ *  lambda_f.2.weight(1 x H) .bias(1)]  -- GladParams.state_dict() order, glad_params.py:10-31 */
+size_t uglad_param_count(int H);
+
+/* (1) covariance: replaces sklearn empirical_covariance in prepare_data.py:342-344.
+ * X[B][M][D] samples -> S[B][D][D] = (X-mean)^T (X-mean) / M.  mean_out[B][D] is required
+ * (it is also the kernel's scratch). */
+int uglad_covariance(const float* X, int B, int M, int D, float* S, float* mean_out, void* stream);
+
+/* symmetric eigensolver used by every stage.  shift_mode 0: A is positive definite (high
+ * relative accuracy, eigenvalues returned as column norms); 1: A is symmetric indefinite.
+ * w[B][D], Vt[B][D][D], info[B][4] = {sweeps, shift, trace(A), sum(w)} (info may be NULL).
+ * scratch: uglad_eigh_scratch_floats(B, D) floats (may be NULL when that returns 0).      */
+size_t uglad_eigh_scratch_floats(int B, int D);
+int uglad_eigh(const float* A, int B, int D, int shift_mode, float* w, float* Vt, float* info,
+               float* scratch, void* stream);
+
+/* prepare_data.py:345-355: eigen-decompose S; if min eig <= 1e-6 add (offset - min) to the
+ * diagonal of S (in place) and to wS.  wS / VtS are reused by every later forward.        */
+int uglad_condition_covariance(float* S, int B, int D, float offset, float* wS, float* VtS,
+                               float* info, float* scratch, void* stream);
+
+/* (2)+(3) the unrolled model.  The workspace holds everything the backward needs
+ * (theta_k1, theta_pred, eigenvectors, eigenvalues per layer) plus scratch.              */
+size_t uglad_workspace_floats(const uglad_dims* d);
+/* float offset of a named workspace region: "theta" (final theta_pred, [B][D][D]),
+ * "theta0", "lambda" ([L]), "normf" ([L] local sums of ||Z-X||_F^2), "sweeps" ([L+1]).
+ * Returns (size_t)-1 for an unknown name.                                                 */
+size_t uglad_workspace_offset(const uglad_dims* d, const char* name);
+
+/* glad.py:106-135: theta_0 and nothing else. */
+int uglad_glad_init_forward(const uglad_dims* d, const float* S, const float* params,
+                            const float* wS, const float* VtS, float* ws, void* stream);
+/* glad.py:136-150, one iteration k (0-based).  Reads normf[k-1] (which the caller has
+ * all-reduced over processes when B_total > B) to form lambda_k, then runs the theta update,
+ * the Z update and leaves the local sum of ||Z-X||_F^2 in normf[k].                        */
+int uglad_glad_layer_forward(const uglad_dims* d, int k, const float* S, const float* params,
+                             float* ws, void* stream);
+/* glad.py:74-150 in one call (single process: B_total == B). */
+int uglad_glad_forward(const uglad_dims* d, const float* S, const float* params,
+                       const float* wS, const float* VtS, float* ws, void* stream);
+/* backward of the above: grad_theta[B][D][D] -> grad_params[uglad_param_count(H)] (local
+ * contribution; the caller all-reduces it over processes).                               */
+int uglad_glad_backward(const uglad_dims* d, const float* S, const float* params,
+                        const float* wS, const float* VtS, float* ws,
+                        const float* grad_theta, float* grad_params, void* stream);
+
+/* (4) main.py:289-315 loss_uGLAD: loss_out[0] = sum_b(-logdet theta_b + <S_b, theta_b>) / Bdiv
+ * and grad_theta (may be NULL) = (-theta^-1 + S) / Bdiv.  S_batch is 1 (broadcast, the
+ * consensus mode of main.py:620-622) or B.  scratch: uglad_loss_scratch_floats(B, D).     */
+size_t uglad_loss_scratch_floats(int B, int D);
+int uglad_glasso_loss(const float* theta, const float* S, int B, int D, int S_batch, float Bdiv,
+                      float* loss_out, float* grad_theta, float* scratch, void* stream);
+
+/* building blocks exported for the parity tests */
+int uglad_z_update(const float* X, const float* S, const float* theta_prev, const float* params,
+                   int H, int B, int D, float* Z, float* normf_out, float* scratch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

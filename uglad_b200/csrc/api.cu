@@ -1,0 +1,304 @@
+// C-ABI of libuglad_b200: orchestration of the kernels into the reference's call graph.
+//   glad.py:74-150    -> uglad_glad_forward / uglad_glad_backward
+//   main.py:289-315   -> uglad_glasso_loss
+//   prepare_data.py:328-356 -> uglad_covariance + uglad_condition_covariance
+#include <stdarg.h>
+#include <string.h>
+#include "kernels.cuh"
+
+namespace uglad {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static inline size_t al4(size_t x) { return (x + 3) & ~(size_t)3; }
+
+struct Ws {
+  size_t theta, X, Vt, beta, sroot, f, snorm, lam, lamfeat, normf, info, part, counter, f0;
+  size_t T1, T2, G0, G1, GF3, rho_part, trh_part, sgb_part, t0_part, eig_scratch, total;
+  size_t n1, n2, nblk;
+  int NPR;
+};
+static Ws ws_layout(const uglad_dims* d) {
+  Ws w;
+  const size_t B = d->B, D = d->D, L = d->L;
+  w.n1 = B * D;
+  w.n2 = B * D * D;
+  w.nblk = (size_t)elem_blocks_per_graph(d->D) * B;
+  w.NPR = rho_param_count(d->H);
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o += al4(n); return r; };
+  w.theta = take((L + 1) * w.n2);
+  w.X = take(L * w.n2);
+  w.Vt = take(L * w.n2);
+  w.beta = take(L * w.n1);
+  w.sroot = take(L * w.n1);
+  w.f = take(L * w.n1);
+  w.snorm = take(L * B);
+  w.lam = take(L);
+  w.lamfeat = take(2 * L);
+  w.normf = take(L);
+  w.info = take(L * B * 4);
+  w.part = take(w.nblk);
+  w.counter = take(4);
+  w.f0 = take(w.n1);
+  w.T1 = take(w.n2);
+  w.T2 = take(w.n2);
+  w.G0 = take(w.n2);
+  w.G1 = take(w.n2);
+  w.GF3 = take(w.n2);
+  w.rho_part = take(L * w.nblk * w.NPR);
+  w.trh_part = take(L * w.nblk);
+  w.sgb_part = take(L * w.nblk);
+  w.t0_part = take(w.nblk);
+  w.eig_scratch = take(eig_scratch_floats(d->B, d->D));
+  w.total = o;
+  return w;
+}
+
+static int check_dims(const uglad_dims* d) {
+  if (!d) { set_error("dims is NULL"); return 1; }
+  if (d->B <= 0 || d->D <= 0 || d->L <= 0) { set_error("bad dims B=%d D=%d L=%d", d->B, d->D, d->L); return 1; }
+  if (d->H <= 0 || d->H > UGLAD_MAX_H) { set_error("H=%d outside [1,%d]", d->H, UGLAD_MAX_H); return 1; }
+  if (d->B_total < d->B) { set_error("B_total=%d < B=%d", d->B_total, d->B); return 1; }
+  return 0;
+}
+
+// C = Vt^T diag(f) Vt   (optionally alpha * (C + E1))
+static int spectral_recon(const float* Vt, const float* f, float* C, int B, int D, float alpha,
+                          const float* E1, long long sE1, cudaStream_t st) {
+  GemmArgs g;
+  g.A = Vt; g.Bm = Vt; g.C = C;
+  g.M = g.N = g.K = D;
+  g.lda = g.ldb = g.ldc = D;
+  g.sA = g.sB = g.sC = (long long)D * D;
+  g.transA = 1; g.transB = 0;
+  g.kscale = f; g.sK = D;
+  g.alpha = alpha; g.E1 = E1; g.sE1 = sE1; g.lde1 = D;
+  return launch_gemm(g, B, st);
+}
+static int bgemm(const float* A, int tA, const float* Bm, int tB, float* C, int B, int D, cudaStream_t st) {
+  GemmArgs g;
+  g.A = A; g.Bm = Bm; g.C = C;
+  g.M = g.N = g.K = D;
+  g.lda = g.ldb = g.ldc = D;
+  g.sA = g.sB = g.sC = (long long)D * D;
+  g.transA = tA; g.transB = tB;
+  return launch_gemm(g, B, st);
+}
+
+int launch_eig(const EigArgs& a, int B, cudaStream_t st) {
+  if (a.D <= UGLAD_SMALL_D_MAX) return launch_eig_small(a, B, st);
+  set_error("eigensolver: D=%d > %d needs the blocked large-D path (not built yet)", a.D, UGLAD_SMALL_D_MAX);
+  return 1;
+}
+size_t eig_scratch_floats(int B, int D) {
+  (void)B;
+  if (D <= UGLAD_SMALL_D_MAX) return 0;
+  return 0;
+}
+
+}  // namespace uglad
+
+using namespace uglad;
+
+extern "C" {
+
+int uglad_abi_version(void) { return UGLAD_ABI_VERSION; }
+const char* uglad_last_error(void) { return g_err; }
+size_t uglad_param_count(int H) { return (size_t)param_layout(H).total; }
+
+int uglad_covariance(const float* X, int B, int M, int D, float* S, float* mean_out, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!X || !S || !mean_out || B <= 0 || M <= 0 || D <= 0) { set_error("covariance: bad arguments"); return 1; }
+  if (launch_colmean(X, B, M, D, mean_out, st)) return 1;
+  GemmArgs g;
+  g.A = X; g.Bm = X; g.C = S;
+  g.M = D; g.N = D; g.K = M;
+  g.lda = D; g.ldb = D; g.ldc = D;
+  g.sA = g.sB = (long long)M * D; g.sC = (long long)D * D;
+  g.transA = 1; g.transB = 0;
+  g.meanA = mean_out; g.meanB = mean_out; g.sMean = D;
+  g.alpha = 1.0f / (float)M;
+  return launch_gemm(g, B, st);
+}
+
+size_t uglad_eigh_scratch_floats(int B, int D) { return eig_scratch_floats(B, D); }
+
+int uglad_eigh(const float* A, int B, int D, int shift_mode, float* w, float* Vt, float* info,
+               float* scratch, void* stream) {
+  if (!A || !w || !Vt || B <= 0 || D <= 0) { set_error("eigh: bad arguments"); return 1; }
+  EigArgs a;
+  a.A = A; a.w = w; a.Vt = Vt; a.info = info; a.scratch = scratch;
+  a.D = D; a.shift_mode = shift_mode; a.tail = TAIL_PLAIN;
+  return launch_eig(a, B, (cudaStream_t)stream);
+}
+
+int uglad_condition_covariance(float* S, int B, int D, float offset, float* wS, float* VtS,
+                               float* info, float* scratch, void* stream) {
+  if (uglad_eigh(S, B, D, 1, wS, VtS, info, scratch, stream)) return 1;
+  return launch_condition(S, wS, B, D, offset, (cudaStream_t)stream);
+}
+
+size_t uglad_workspace_floats(const uglad_dims* d) {
+  if (check_dims(d)) return 0;
+  return ws_layout(d).total;
+}
+
+size_t uglad_workspace_offset(const uglad_dims* d, const char* name) {
+  if (check_dims(d) || !name) return (size_t)-1;
+  const Ws w = ws_layout(d);
+  if (!strcmp(name, "theta")) return w.theta + (size_t)d->L * w.n2;
+  if (!strcmp(name, "theta0")) return w.theta;
+  if (!strcmp(name, "theta_all")) return w.theta;
+  if (!strcmp(name, "X")) return w.X;
+  if (!strcmp(name, "Vt")) return w.Vt;
+  if (!strcmp(name, "beta")) return w.beta;
+  if (!strcmp(name, "lambda")) return w.lam;
+  if (!strcmp(name, "normf")) return w.normf;
+  if (!strcmp(name, "info")) return w.info;
+  set_error("workspace_offset: unknown region '%s'", name);
+  return (size_t)-1;
+}
+
+int uglad_glad_init_forward(const uglad_dims* d, const float* S, const float* params,
+                            const float* wS, const float* VtS, float* ws, void* stream) {
+  if (check_dims(d)) return 1;
+  if (!S || !params || !ws) { set_error("glad_init_forward: NULL pointer"); return 1; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const Ws w = ws_layout(d);
+  UGLAD_CUDA(cudaMemsetAsync(ws + w.counter, 0, 4 * sizeof(float), st));
+  if (d->init_diag == 1) return launch_theta_init_diag(S, params, d->B, d->D, ws + w.theta, st);
+  if (!wS || !VtS) { set_error("glad_init_forward: INIT_DIAG=0 needs the eigen-decomposition of S"); return 1; }
+  if (launch_init_f(wS, params, d->B, d->D, ws + w.f0, st)) return 1;
+  return spectral_recon(VtS, ws + w.f0, ws + w.theta, d->B, d->D, 1.f, nullptr, 0, st);
+}
+
+int uglad_glad_layer_forward(const uglad_dims* d, int k, const float* S, const float* params,
+                             float* ws, void* stream) {
+  if (check_dims(d)) return 1;
+  if (k < 0 || k >= d->L) { set_error("glad_layer_forward: k=%d outside [0,%d)", k, d->L); return 1; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const Ws w = ws_layout(d);
+  const int B = d->B, D = d->D;
+  float* theta_prev = ws + w.theta + (size_t)k * w.n2;
+  float* theta_next = ws + w.theta + (size_t)(k + 1) * w.n2;
+  float* Xk = ws + w.X + (size_t)k * w.n2;
+  float* Vk = ws + w.Vt + (size_t)k * w.n2;
+  float* fk = ws + w.f + (size_t)k * w.n1;
+  if (launch_lambda_step(k, params, d->H, d->lambda_init, d->B_total, ws + w.normf, ws + w.lam,
+                         ws + w.lamfeat, st)) return 1;
+  EigArgs a;
+  a.build = 1; a.S = S; a.Theta = theta_prev; a.lam = ws + w.lam + k; a.strideS = (long long)D * D;
+  a.w = ws + w.beta + (size_t)k * w.n1; a.Vt = Vk; a.info = ws + w.info + (size_t)k * B * 4;
+  a.f = fk; a.sroot = ws + w.sroot + (size_t)k * w.n1; a.snorm = ws + w.snorm + (size_t)k * B;
+  a.scratch = ws + w.eig_scratch;
+  a.D = D; a.shift_mode = 1; a.tail = TAIL_LAYER; a.exact_sqrt = d->exact_sqrt;
+  if (launch_eig(a, B, st)) return 1;
+  if (spectral_recon(Vk, fk, Xk, B, D, 1.f, nullptr, 0, st)) return 1;
+  return launch_z_update_fwd(Xk, S, theta_prev, params, d->H, B, D, theta_next, ws + w.part,
+                             ws + w.normf + k, reinterpret_cast<unsigned*>(ws + w.counter), st);
+}
+
+int uglad_glad_forward(const uglad_dims* d, const float* S, const float* params,
+                       const float* wS, const float* VtS, float* ws, void* stream) {
+  if (check_dims(d)) return 1;
+  if (d->B_total != d->B) { set_error("glad_forward: B_total != B; drive the layers from the host and all-reduce normf"); return 1; }
+  if (uglad_glad_init_forward(d, S, params, wS, VtS, ws, stream)) return 1;
+  for (int k = 0; k < d->L; ++k)
+    if (uglad_glad_layer_forward(d, k, S, params, ws, stream)) return 1;
+  return 0;
+}
+
+int uglad_glad_backward(const uglad_dims* d, const float* S, const float* params,
+                        const float* wS, const float* VtS, float* ws,
+                        const float* grad_theta, float* grad_params, void* stream) {
+  (void)wS; (void)VtS;
+  if (check_dims(d)) return 1;
+  if (!S || !params || !ws || !grad_theta || !grad_params) { set_error("glad_backward: NULL pointer"); return 1; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const Ws w = ws_layout(d);
+  const int B = d->B, D = d->D, L = d->L;
+  float* T1 = ws + w.T1;
+  float* T2 = ws + w.T2;
+  float* GF3 = ws + w.GF3;
+  float* Gbuf[2] = {ws + w.G0, ws + w.G1};
+  const float* G = grad_theta;
+  for (int k = L - 1; k >= 0; --k) {
+    const float* theta_prev = ws + w.theta + (size_t)k * w.n2;
+    const float* Xk = ws + w.X + (size_t)k * w.n2;
+    const float* Vk = ws + w.Vt + (size_t)k * w.n2;
+    if (launch_z_update_bwd(G, Xk, S, theta_prev, params, d->H, B, D, T1, GF3,
+                            ws + w.rho_part + (size_t)k * w.nblk * w.NPR, st)) return 1;
+    if (bgemm(T1, 0, Vk, 1, T2, B, D, st)) return 1;   // T2 = GX V
+    if (bgemm(Vk, 0, T2, 0, T1, B, D, st)) return 1;   // T1 = V^T GX V
+    if (launch_phi(T1, ws + w.beta + (size_t)k * w.n1, ws + w.sroot + (size_t)k * w.n1,
+                   ws + w.snorm + (size_t)k * B, ws + w.lam + k, d->exact_sqrt, B, D,
+                   ws + w.trh_part + (size_t)k * w.nblk, st)) return 1;
+    if (bgemm(T1, 0, Vk, 0, T2, B, D, st)) return 1;   // T2 = W V^T
+    if (bgemm(Vk, 1, T2, 0, T1, B, D, st)) return 1;   // T1 = V W V^T = grad b
+    float* Gn = Gbuf[k & 1];
+    if (launch_gb_finish(T1, GF3, S, B, D, Gn, ws + w.sgb_part + (size_t)k * w.nblk, st)) return 1;
+    G = Gn;
+  }
+  // theta_0 = (S + t I)^-1  ->  d/dt = -theta_0^2 ;  diag variant -> -theta_0,ii^2
+  if (d->init_diag == 1) {
+    if (launch_dot_partial(G, ws + w.theta, B, D, 1, ws + w.t0_part, st)) return 1;
+  } else {
+    if (bgemm(ws + w.theta, 0, ws + w.theta, 0, T1, B, D, st)) return 1;
+    if (launch_dot_partial(G, T1, B, D, 0, ws + w.t0_part, st)) return 1;
+  }
+  return launch_finalize_grads(params, d->H, L, (int)w.nblk, ws + w.rho_part, ws + w.trh_part,
+                               ws + w.sgb_part, ws + w.t0_part, ws + w.lam, ws + w.lamfeat,
+                               grad_params, st);
+}
+
+size_t uglad_loss_scratch_floats(int B, int D) {
+  const size_t n2 = (size_t)B * D * D, n1 = (size_t)B * D;
+  return al4(n2) + 2 * al4(n1) + 2 * al4(B) + al4(4 * (size_t)B) + 8 + al4(eig_scratch_floats(B, D));
+}
+
+int uglad_glasso_loss(const float* theta, const float* S, int B, int D, int S_batch, float Bdiv,
+                      float* loss_out, float* grad_theta, float* scratch, void* stream) {
+  if (!theta || !S || !loss_out || !scratch || B <= 0 || D <= 0) { set_error("glasso_loss: bad arguments"); return 1; }
+  if (S_batch != 1 && S_batch != B) { set_error("glasso_loss: S_batch=%d must be 1 or B=%d", S_batch, B); return 1; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n2 = (size_t)B * D * D, n1 = (size_t)B * D;
+  float* Vt = scratch;
+  float* w = Vt + al4(n2);
+  float* f = w + al4(n1);
+  float* logdet = f + al4(n1);
+  float* lossb = logdet + al4(B);
+  float* info = lossb + al4(B);
+  float* counter = info + al4(4 * (size_t)B);
+  float* escr = counter + 8;
+  UGLAD_CUDA(cudaMemsetAsync(counter, 0, 4 * sizeof(float), st));
+  EigArgs a;
+  a.A = theta; a.w = w; a.Vt = Vt; a.info = info; a.f = f; a.snorm = logdet; a.scratch = escr;
+  a.D = D; a.shift_mode = 0; a.tail = TAIL_LOSS;
+  if (launch_eig(a, B, st)) return 1;
+  const long long sS = (S_batch == 1) ? 0 : (long long)D * D;
+  if (launch_loss_terms(theta, S, sS, logdet, B, D, Bdiv, lossb, loss_out,
+                        reinterpret_cast<unsigned*>(counter), st)) return 1;
+  if (grad_theta) return spectral_recon(Vt, f, grad_theta, B, D, 1.0f / Bdiv, S, sS, st);
+  return 0;
+}
+
+int uglad_z_update(const float* X, const float* S, const float* theta_prev, const float* params,
+                   int H, int B, int D, float* Z, float* normf_out, float* scratch, void* stream) {
+  if (!X || !S || !theta_prev || !params || !Z || !normf_out || !scratch) { set_error("z_update: NULL pointer"); return 1; }
+  if (H <= 0 || H > UGLAD_MAX_H) { set_error("z_update: H=%d outside [1,%d]", H, UGLAD_MAX_H); return 1; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nblk = (size_t)elem_blocks_per_graph(D) * B;
+  float* counter = scratch + al4(nblk);
+  UGLAD_CUDA(cudaMemsetAsync(counter, 0, 4 * sizeof(float), st));
+  return launch_z_update_fwd(X, S, theta_prev, params, H, B, D, Z, scratch, normf_out,
+                             reinterpret_cast<unsigned*>(counter), st);
+}
+
+}  // extern "C"

@@ -1,0 +1,485 @@
+// Entrywise and reduction kernels of the unrolled GLAD cell and its backward (sm_100a).
+// All reductions are deterministic: per-block partials are written to a buffer and summed in
+// index order (by the last block to finish, or by the finalize kernel) in double precision.
+#include "kernels.cuh"
+
+namespace uglad {
+
+constexpr int EW_THREADS = 256;
+
+int elem_blocks_per_graph(int D) {
+  const long long n = (long long)D * D;
+  long long b = (n + 2047) / 2048;
+  if (b < 1) b = 1;
+  if (b > 64) b = 64;
+  return (int)b;
+}
+int rho_param_count(int H) { return H * UGLAD_NF + H + H * H + H + H + 1; }
+
+__device__ __forceinline__ void load_params_smem(float* sw, const float* params, int total) {
+  for (int i = threadIdx.x; i < total; i += blockDim.x) sw[i] = params[i];
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// lambda_k = lambda_f([normF_{k-1} / B_total, lambda_{k-1}])   (glad.py:135,146-150,
+// glad_params.py:79-91).  One warp.  Stores the input features for the backward.
+__global__ void lambda_step_kernel(int k, const float* params, int H, float lambda_init,
+                                   int B_total, const float* normf, float* lam, float* lamfeat) {
+  if (threadIdx.x != 0) return;
+  const ParamLayout pl = param_layout(H);
+  float x0, x1;
+  if (k == 0) {
+    x0 = lambda_init;
+    x1 = 0.f;
+  } else {
+    x0 = normf[k - 1] / (float)B_total;
+    x1 = lam[k - 1];
+  }
+  float o = params[pl.lb2];
+  for (int i = 0; i < H; ++i) {
+    const float h = tanhf(fmaf(params[pl.lW1 + 2 * i], x0, fmaf(params[pl.lW1 + 2 * i + 1], x1, params[pl.lb1 + i])));
+    o = fmaf(params[pl.lW2 + i], h, o);
+  }
+  lam[k] = sigmoidf_(o);
+  lamfeat[2 * k] = x0;
+  lamfeat[2 * k + 1] = x1;
+}
+int launch_lambda_step(int k, const float* params, int H, float lambda_init, int B_total,
+                       const float* normf, float* lam, float* lamfeat, cudaStream_t st) {
+  lambda_step_kernel<<<1, 32, 0, st>>>(k, params, H, lambda_init, B_total, normf, lam, lamfeat);
+  UGLAD_CHECK_LAUNCH("lambda_step_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Z update (glad_params.py:56-77) fused with the rho_l1 MLP and the Frobenius term of
+// glad.py:147.  grid (blocks_per_graph, B).
+template <int HT>
+__global__ void __launch_bounds__(EW_THREADS) z_update_fwd_kernel(
+    const float* __restrict__ X, const float* __restrict__ S, const float* __restrict__ Tprev,
+    const float* __restrict__ params, int H, int n, float* __restrict__ Z, float* part,
+    float* normf_out, unsigned* counter) {
+  __shared__ float sw[1 + UGLAD_MAX_H * (UGLAD_NF + 4 + UGLAD_MAX_H) + 1 + 64];
+  __shared__ float red[32];
+  __shared__ double redd[32];
+  __shared__ bool s_last;
+  const ParamLayout pl = param_layout(HT ? HT : H);
+  load_params_smem(sw, params, pl.lW1);  // rho part only
+  RhoMLP<HT> mlp(sw, H);
+  const size_t base = (size_t)blockIdx.y * n;
+  float acc = 0.f;
+  float h1[RhoMLP<HT>::HM], h2[RhoMLP<HT>::HM];
+  for (int i = blockIdx.x * EW_THREADS + threadIdx.x; i < n; i += gridDim.x * EW_THREADS) {
+    const float x = X[base + i];
+    const float rho = mlp.forward(x, S[base + i], Tprev[base + i], h1, h2);
+    const float z = soft_threshold(x, rho);
+    Z[base + i] = z;
+    const float d = z - x;
+    acc = fmaf(d, d, acc);
+  }
+  const float tot = block_sum(acc, red);
+  const unsigned nblocks = gridDim.x * gridDim.y;
+  if (threadIdx.x == 0) {
+    part[blockIdx.y * gridDim.x + blockIdx.x] = tot;
+    __threadfence();
+    const unsigned ticket = atomicAdd(counter, 1u);
+    s_last = (ticket == nblocks - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    double s = 0.0;
+    for (unsigned i = threadIdx.x; i < nblocks; i += EW_THREADS) s += (double)((volatile float*)part)[i];
+    s = block_sum_d(s, redd);
+    if (threadIdx.x == 0) {
+      normf_out[0] = (float)s;
+      *counter = 0u;
+    }
+  }
+}
+int launch_z_update_fwd(const float* X, const float* S, const float* Tprev, const float* params,
+                        int H, int B, int D, float* Z, float* part, float* normf_out,
+                        unsigned* counter, cudaStream_t st) {
+  dim3 grid(elem_blocks_per_graph(D), B);
+  const int n = D * D;
+  if (H == 3)
+    z_update_fwd_kernel<3><<<grid, EW_THREADS, 0, st>>>(X, S, Tprev, params, H, n, Z, part, normf_out, counter);
+  else
+    z_update_fwd_kernel<0><<<grid, EW_THREADS, 0, st>>>(X, S, Tprev, params, H, n, Z, part, normf_out, counter);
+  UGLAD_CHECK_LAUNCH("z_update_fwd_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Backward of the Z update.  Z = sign(X) relu(|X| - rho(X,S,T)):
+//   dZ/dX = 1[|X|>rho] * (1 - sign(X) drho/dX),  dZ/dT = -1[..] sign(X) drho/dT,
+// and rho_l1's weight gradients are accumulated per thread, reduced per block and written
+// to rho_part[block][NPR].
+template <int HT>
+__global__ void __launch_bounds__(EW_THREADS) z_update_bwd_kernel(
+    const float* __restrict__ GZ, const float* __restrict__ X, const float* __restrict__ S,
+    const float* __restrict__ Tprev, const float* __restrict__ params, int H, int n,
+    float* __restrict__ GX, float* __restrict__ GF3, float* rho_part) {
+  constexpr int HM = RhoMLP<HT>::HM;
+  constexpr int NPR_MAX = HM * UGLAD_NF + HM + HM * HM + HM + HM + 1;
+  __shared__ float sw[1 + UGLAD_MAX_H * (UGLAD_NF + 4 + UGLAD_MAX_H) + 1 + 64];
+  __shared__ float red[32];
+  const int Hh = HT ? HT : H;
+  const ParamLayout pl = param_layout(Hh);
+  load_params_smem(sw, params, pl.lW1);
+  RhoMLP<HT> mlp(sw, H);
+  const int NPR = Hh * UGLAD_NF + Hh + Hh * Hh + Hh + Hh + 1;
+  // accumulator layout follows the packed parameter order starting at rW1
+  float g[NPR_MAX];
+#pragma unroll
+  for (int i = 0; i < NPR_MAX; ++i) g[i] = 0.f;
+  const int oW1 = 0, ob1 = Hh * UGLAD_NF, oW2 = ob1 + Hh, ob2 = oW2 + Hh * Hh, oW3 = ob2 + Hh, ob3 = oW3 + Hh;
+  const size_t base = (size_t)blockIdx.y * n;
+  float h1[HM], h2[HM], d2[HM], d1[HM];
+  for (int i = blockIdx.x * EW_THREADS + threadIdx.x; i < n; i += gridDim.x * EW_THREADS) {
+    const float x = X[base + i], s = S[base + i], t = Tprev[base + i], gz = GZ[base + i];
+    const float rho = mlp.forward(x, s, t, h1, h2);
+    const bool act = (fabsf(x) - rho) > 0.f;
+    float gx = 0.f, gt = 0.f;
+    if (act && gz != 0.f) {
+      const float sgn = (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f);
+      const float go = -sgn * gz * rho * (1.f - rho);  // grad wrt the pre-sigmoid output
+      g[ob3] += go;
+#pragma unroll
+      for (int j = 0; j < HM; ++j)
+        if (j < Hh) {
+          g[oW3 + j] = fmaf(go, h2[j], g[oW3 + j]);
+          d2[j] = go * sw[pl.rW3 + j] * (1.f - h2[j] * h2[j]);
+          g[ob2 + j] += d2[j];
+        }
+#pragma unroll
+      for (int j = 0; j < HM; ++j)
+        if (j < Hh) {
+          float a = 0.f;
+#pragma unroll
+          for (int o = 0; o < HM; ++o)
+            if (o < Hh) {
+              g[oW2 + o * Hh + j] = fmaf(d2[o], h1[j], g[oW2 + o * Hh + j]);
+              a = fmaf(d2[o], sw[pl.rW2 + o * Hh + j], a);
+            }
+          d1[j] = a * (1.f - h1[j] * h1[j]);
+          g[ob1 + j] += d1[j];
+        }
+      float fx = 0.f, ft = 0.f;
+#pragma unroll
+      for (int j = 0; j < HM; ++j)
+        if (j < Hh) {
+          g[oW1 + j * UGLAD_NF + 0] = fmaf(d1[j], x, g[oW1 + j * UGLAD_NF + 0]);
+          g[oW1 + j * UGLAD_NF + 1] = fmaf(d1[j], s, g[oW1 + j * UGLAD_NF + 1]);
+          g[oW1 + j * UGLAD_NF + 2] = fmaf(d1[j], t, g[oW1 + j * UGLAD_NF + 2]);
+          fx = fmaf(d1[j], sw[pl.rW1 + j * UGLAD_NF + 0], fx);
+          ft = fmaf(d1[j], sw[pl.rW1 + j * UGLAD_NF + 2], ft);
+        }
+      gx = gz + fx;
+      gt = ft;
+    }
+    GX[base + i] = gx;
+    GF3[base + i] = gt;
+  }
+  float* out = rho_part + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * NPR;
+#pragma unroll
+  for (int p = 0; p < NPR_MAX; ++p) {
+    if (p < NPR) {
+      const float tot = block_sum(g[p], red);
+      if (threadIdx.x == 0) out[p] = tot;
+    }
+  }
+}
+int launch_z_update_bwd(const float* GZ, const float* X, const float* S, const float* Tprev,
+                        const float* params, int H, int B, int D, float* GX, float* GF3,
+                        float* rho_part, cudaStream_t st) {
+  dim3 grid(elem_blocks_per_graph(D), B);
+  const int n = D * D;
+  if (H == 3)
+    z_update_bwd_kernel<3><<<grid, EW_THREADS, 0, st>>>(GZ, X, S, Tprev, params, H, n, GX, GF3, rho_part);
+  else
+    z_update_bwd_kernel<0><<<grid, EW_THREADS, 0, st>>>(GZ, X, S, Tprev, params, H, n, GX, GF3, rho_part);
+  UGLAD_CHECK_LAUNCH("z_update_bwd_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// F-matrix of the theta update in the eigenbasis of b (in place on Gt = V^T G V):
+//   x = V f(beta) V^T with f = (s - beta)/2 and s the Newton-Schulz root of beta^2 + 4/lambda.
+//   torch_sqrtm.py:31-45 gives grad wrt (b^T b + 4/lambda I) as  H = C * (Gt/2),
+//   C_ij = 0.5 * prod_t 0.5(3 - a_i^2 - a_j^2 + a_i a_j) / ||s||   (exact: 1/(s_i + s_j));
+//   d(b^T b) -> (beta_i + beta_j) H ;  the -b/2 term -> -Gt/2.
+// Also reduces trace(H) (gradient of the 4/lambda I term) per block.
+__global__ void __launch_bounds__(EW_THREADS) phi_kernel(
+    float* __restrict__ Gt, const float* __restrict__ beta, const float* __restrict__ sroot,
+    const float* __restrict__ snorm, int exact_sqrt, int D, float* trh_part) {
+  __shared__ float red[32];
+  const int b = blockIdx.y;
+  const int n = D * D;
+  const float* be = beta + (size_t)b * D;
+  const float* sr = sroot + (size_t)b * D;
+  const float nrm = snorm[b];
+  const float inv_nrm = 1.f / nrm;
+  float tr = 0.f;
+  for (int idx = blockIdx.x * EW_THREADS + threadIdx.x; idx < n; idx += gridDim.x * EW_THREADS) {
+    const int i = idx / D, j = idx - i * D;
+    const float gt = Gt[(size_t)b * n + idx];
+    float C;
+    if (exact_sqrt)
+      C = 1.f / (sr[i] + sr[j]);
+    else
+      C = 0.5f * ns_backward_factor(sr[i] * inv_nrm, sr[j] * inv_nrm) * inv_nrm;
+    const float Hh = 0.5f * C * gt;
+    if (i == j) tr += Hh;
+    Gt[(size_t)b * n + idx] = (be[i] + be[j]) * Hh - 0.5f * gt;
+  }
+  const float tot = block_sum(tr, red);
+  if (threadIdx.x == 0) trh_part[blockIdx.y * gridDim.x + blockIdx.x] = tot;
+}
+int launch_phi(float* Gt, const float* beta, const float* sroot, const float* snorm,
+               const float* lam, int exact_sqrt, int B, int D, float* trh_part, cudaStream_t st) {
+  (void)lam;
+  dim3 grid(elem_blocks_per_graph(D), B);
+  phi_kernel<<<grid, EW_THREADS, 0, st>>>(Gt, beta, sroot, snorm, exact_sqrt, D, trh_part);
+  UGLAD_CHECK_LAUNCH("phi_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// b = S/lambda - theta_prev:  grad theta_prev = GF3 - Gb ;  <S, Gb> feeds grad lambda.
+__global__ void __launch_bounds__(EW_THREADS) gb_finish_kernel(
+    const float* __restrict__ Gb, const float* __restrict__ GF3, const float* __restrict__ S,
+    int n, float* __restrict__ Gnext, float* sgb_part) {
+  __shared__ float red[32];
+  const size_t base = (size_t)blockIdx.y * n;
+  float acc = 0.f;
+  for (int i = blockIdx.x * EW_THREADS + threadIdx.x; i < n; i += gridDim.x * EW_THREADS) {
+    const float gb = Gb[base + i];
+    acc = fmaf(S[base + i], gb, acc);
+    Gnext[base + i] = GF3[base + i] - gb;
+  }
+  const float tot = block_sum(acc, red);
+  if (threadIdx.x == 0) sgb_part[blockIdx.y * gridDim.x + blockIdx.x] = tot;
+}
+int launch_gb_finish(const float* Gb, const float* GF3, const float* S, int B, int D, float* Gnext,
+                     float* sgb_part, cudaStream_t st) {
+  dim3 grid(elem_blocks_per_graph(D), B);
+  gb_finish_kernel<<<grid, EW_THREADS, 0, st>>>(Gb, GF3, S, D * D, Gnext, sgb_part);
+  UGLAD_CHECK_LAUNCH("gb_finish_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// theta_0 helpers (glad.py:106-117)
+__global__ void init_f_kernel(const float* wS, const float* params, int n, float* f0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) f0[i] = 1.f / (wS[i] + params[0]);
+}
+int launch_init_f(const float* wS, const float* params, int B, int D, float* f0, cudaStream_t st) {
+  const int n = B * D;
+  init_f_kernel<<<(n + 255) / 256, 256, 0, st>>>(wS, params, n, f0);
+  UGLAD_CHECK_LAUNCH("init_f_kernel");
+  return 0;
+}
+__global__ void theta_init_diag_kernel(const float* S, const float* params, int D, float* theta0) {
+  const size_t base = (size_t)blockIdx.y * D * D;
+  const int n = D * D;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+    const int i = idx / D, j = idx - i * D;
+    theta0[base + idx] = (i == j) ? 1.f / (S[base + idx] + params[0]) : 0.f;
+  }
+}
+int launch_theta_init_diag(const float* S, const float* params, int B, int D, float* theta0,
+                           cudaStream_t st) {
+  dim3 grid(elem_blocks_per_graph(D), B);
+  theta_init_diag_kernel<<<grid, EW_THREADS, 0, st>>>(S, params, D, theta0);
+  UGLAD_CHECK_LAUNCH("theta_init_diag_kernel");
+  return 0;
+}
+
+// per-block partials of <A, B>  (diag_sq: sum_i A_ii * B_ii^2, the INIT_DIAG=1 offset gradient)
+__global__ void __launch_bounds__(EW_THREADS) dot_partial_kernel(
+    const float* __restrict__ A, const float* __restrict__ Bm, int D, int diag_sq, float* part) {
+  __shared__ float red[32];
+  const int n = D * D;
+  const size_t base = (size_t)blockIdx.y * n;
+  float acc = 0.f;
+  if (diag_sq) {
+    for (int i = blockIdx.x * EW_THREADS + threadIdx.x; i < D; i += gridDim.x * EW_THREADS) {
+      const float t = Bm[base + (size_t)i * D + i];
+      acc = fmaf(A[base + (size_t)i * D + i], t * t, acc);
+    }
+  } else {
+    for (int i = blockIdx.x * EW_THREADS + threadIdx.x; i < n; i += gridDim.x * EW_THREADS)
+      acc = fmaf(A[base + i], Bm[base + i], acc);
+  }
+  const float tot = block_sum(acc, red);
+  if (threadIdx.x == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = tot;
+}
+int launch_dot_partial(const float* A, const float* Bm, int B, int D, int diag_sq, float* part,
+                       cudaStream_t st) {
+  dim3 grid(elem_blocks_per_graph(D), B);
+  dot_partial_kernel<<<grid, EW_THREADS, 0, st>>>(A, Bm, D, diag_sq, part);
+  UGLAD_CHECK_LAUNCH("dot_partial_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Sum every partial buffer into the packed gradient vector.
+//   block p < NPR            : rho_l1 parameter p, summed over L * nblk partial rows
+//   block NPR                : theta_init_offset  = -sum(t0_part)
+//   block NPR + 1            : lambda_f: g_lambda_k = -(4 tr(H_k) + <S, Gb_k>) / lambda_k^2,
+//                              chained through the MLP at the saved features (inputs detached)
+__global__ void __launch_bounds__(EW_THREADS) finalize_grads_kernel(
+    const float* params, int H, int L, int nblk, const float* rho_part, const float* trh_part,
+    const float* sgb_part, const float* t0_part, const float* lam, const float* lamfeat,
+    float* grad_params) {
+  __shared__ double redd[32];
+  __shared__ double s_gl[256];
+  const ParamLayout pl = param_layout(H);
+  const int NPR = pl.lW1 - pl.rW1;
+  const int blk = blockIdx.x;
+  if (blk < NPR) {
+    double s = 0.0;
+    const size_t rows = (size_t)L * nblk;
+    for (size_t r = threadIdx.x; r < rows; r += EW_THREADS) s += (double)rho_part[r * NPR + blk];
+    s = block_sum_d(s, redd);
+    if (threadIdx.x == 0) grad_params[pl.rW1 + blk] = (float)s;
+  } else if (blk == NPR) {
+    double s = 0.0;
+    for (int r = threadIdx.x; r < nblk; r += EW_THREADS) s += (double)t0_part[r];
+    s = block_sum_d(s, redd);
+    if (threadIdx.x == 0) grad_params[pl.t0] = (float)(-s);
+  } else {
+    for (int k = 0; k < L; ++k) {
+      double s = 0.0;
+      for (int r = threadIdx.x; r < nblk; r += EW_THREADS)
+        s += 4.0 * (double)trh_part[(size_t)k * nblk + r] + (double)sgb_part[(size_t)k * nblk + r];
+      s = block_sum_d(s, redd);
+      if (threadIdx.x == 0) {
+        const double l = lam[k];
+        s_gl[k & 255] = -s / (l * l);
+      }
+      __syncthreads();
+      // chain through lambda_f at (x0, x1) = lamfeat[k]; one thread, 4H+1 outputs
+      if (threadIdx.x == 0) {
+        const double gl = s_gl[k & 255];
+        const double x0 = lamfeat[2 * k], x1 = lamfeat[2 * k + 1];
+        const double o = lam[k];
+        const double go = gl * o * (1.0 - o);
+        for (int i = 0; i < H; ++i) {
+          const double h = tanh((double)params[pl.lW1 + 2 * i] * x0 + (double)params[pl.lW1 + 2 * i + 1] * x1 + (double)params[pl.lb1 + i]);
+          const double d1 = go * (double)params[pl.lW2 + i] * (1.0 - h * h);
+          const float first = (k == 0) ? 0.f : 1.f;
+          grad_params[pl.lW2 + i] = first * grad_params[pl.lW2 + i] + (float)(go * h);
+          grad_params[pl.lW1 + 2 * i] = first * grad_params[pl.lW1 + 2 * i] + (float)(d1 * x0);
+          grad_params[pl.lW1 + 2 * i + 1] = first * grad_params[pl.lW1 + 2 * i + 1] + (float)(d1 * x1);
+          grad_params[pl.lb1 + i] = first * grad_params[pl.lb1 + i] + (float)d1;
+        }
+        grad_params[pl.lb2] = ((k == 0) ? 0.f : grad_params[pl.lb2]) + (float)go;
+      }
+      __syncthreads();
+    }
+  }
+}
+int launch_finalize_grads(const float* params, int H, int L, int nblk, const float* rho_part,
+                          const float* trh_part, const float* sgb_part, const float* t0_part,
+                          const float* lam, const float* lamfeat, float* grad_params,
+                          cudaStream_t st) {
+  const int NPR = rho_param_count(H);
+  finalize_grads_kernel<<<NPR + 2, EW_THREADS, 0, st>>>(params, H, L, nblk, rho_part, trh_part, sgb_part,
+                                                        t0_part, lam, lamfeat, grad_params);
+  UGLAD_CHECK_LAUNCH("finalize_grads_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// loss_b = -logdet_b + <S_b, theta_b>  (main.py:307-315); the last block sums over graphs.
+__global__ void __launch_bounds__(EW_THREADS) loss_terms_kernel(
+    const float* __restrict__ theta, const float* __restrict__ S, long long strideS,
+    const float* __restrict__ logdet, int n, float Bdiv, float* lossb, float* loss_out,
+    unsigned* counter) {
+  __shared__ double redd[32];
+  __shared__ bool s_last;
+  const int b = blockIdx.x;
+  const float* T = theta + (size_t)b * n;
+  const float* Sb = S + (size_t)b * strideS;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += EW_THREADS) acc += (double)Sb[i] * (double)T[i];
+  acc = block_sum_d(acc, redd);
+  if (threadIdx.x == 0) {
+    lossb[b] = (float)(acc - (double)logdet[b]);
+    __threadfence();
+    const unsigned ticket = atomicAdd(counter, 1u);
+    s_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    double s = 0.0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += EW_THREADS) s += (double)((volatile float*)lossb)[i];
+    s = block_sum_d(s, redd);
+    if (threadIdx.x == 0) {
+      loss_out[0] = (float)(s / (double)Bdiv);
+      *counter = 0u;
+    }
+  }
+}
+int launch_loss_terms(const float* theta, const float* S, long long strideS, const float* logdet,
+                      int B, int D, float Bdiv, float* lossb, float* loss_out, unsigned* counter,
+                      cudaStream_t st) {
+  loss_terms_kernel<<<B, EW_THREADS, 0, st>>>(theta, S, strideS, logdet, D * D, Bdiv, lossb, loss_out, counter);
+  UGLAD_CHECK_LAUNCH("loss_terms_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// covariance helpers
+// column means of X[B][M][D]: block (32 x 8), thread column = contiguous dimension
+__global__ void colmean_kernel(const float* __restrict__ X, int M, int D, float* mean) {
+  __shared__ double sm[8][33];
+  const int b = blockIdx.y;
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  const float* Xb = X + (size_t)b * M * D;
+  double acc = 0.0;
+  if (col < D)
+    for (int r = threadIdx.y; r < M; r += 8) acc += (double)Xb[(size_t)r * D + col];
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < D) {
+    double s = 0.0;
+    for (int r = 0; r < 8; ++r) s += sm[r][threadIdx.x];
+    mean[(size_t)b * D + col] = (float)(s / (double)M);
+  }
+}
+int launch_colmean(const float* X, int B, int M, int D, float* mean, cudaStream_t st) {
+  dim3 grid((D + 31) / 32, B), block(32, 8);
+  colmean_kernel<<<grid, block, 0, st>>>(X, M, D, mean);
+  UGLAD_CHECK_LAUNCH("colmean_kernel");
+  return 0;
+}
+
+// prepare_data.py:348-350: if min eig <= 1e-6, S += (offset - min) I (and the eigenvalues move
+// by the same amount, the eigenvectors do not).  One block per graph.
+__global__ void condition_kernel(float* S, float* wS, int D, float offset) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  float mn = INFINITY;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) mn = fminf(mn, wS[(size_t)b * D + i]);
+  mn = -block_max(-mn, red);
+  if (mn <= 1e-6f) {
+    const float add = offset - mn;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+      wS[(size_t)b * D + i] += add;
+      S[(size_t)b * D * D + (size_t)i * D + i] += add;
+    }
+  }
+}
+int launch_condition(float* S, float* wS, int B, int D, float offset, cudaStream_t st) {
+  condition_kernel<<<B, 256, 0, st>>>(S, wS, D, offset);
+  UGLAD_CHECK_LAUNCH("condition_kernel");
+  return 0;
+}
+
+}  // namespace uglad

@@ -1,0 +1,86 @@
+// Internal launcher declarations shared between the .cu files of libuglad_b200.
+#pragma once
+#include "common.cuh"
+
+namespace uglad {
+
+// largest D handled by the one-CTA shared-memory eigensolver: ld*D*4 B + ~1.5 KB <= 227 KB
+#define UGLAD_SMALL_D_MAX 232
+
+enum EigTail { TAIL_PLAIN = 0, TAIL_LAYER = 1, TAIL_LOSS = 2 };
+
+struct EigArgs {
+  const float* A = nullptr;      // [B][D][D] symmetric input (build == 0)
+  const float* S = nullptr;      // build == 1: input is S/lam - Theta (glad.py:139)
+  const float* Theta = nullptr;
+  const float* lam = nullptr;    // device scalar lambda_k (build / TAIL_LAYER)
+  long long strideS = 0;
+  float* w = nullptr;            // [B][D] eigenvalues
+  float* Vt = nullptr;           // [B][D][D] rows are eigenvectors
+  float* info = nullptr;         // [B][4] {sweeps, shift, trace, sum(w)} or null
+  float* f = nullptr;            // TAIL_LAYER: (s-beta)/2 ; TAIL_LOSS: -1/eig
+  float* sroot = nullptr;        // TAIL_LAYER: eigenvalues s of the (Newton-Schulz) root
+  float* snorm = nullptr;        // TAIL_LAYER: [B] ||s||_2 ; TAIL_LOSS: [B] logdet
+  float* scratch = nullptr;      // large-D path only
+  int D = 0, ld = 0, build = 0, shift_mode = 1, tail = TAIL_PLAIN, exact_sqrt = 0;
+  int max_sweeps = 40;
+  float tol = 1e-6f;
+};
+int launch_eig_small(const EigArgs& a, int B, cudaStream_t st);
+int launch_eig(const EigArgs& a, int B, cudaStream_t st);  // dispatch on D
+size_t eig_scratch_floats(int B, int D);
+
+// ---- batched SGEMM ------------------------------------------------------------------------
+struct GemmArgs {
+  const float* A = nullptr;
+  const float* Bm = nullptr;
+  float* C = nullptr;
+  int M = 0, N = 0, K = 0;
+  int lda = 0, ldb = 0, ldc = 0;
+  long long sA = 0, sB = 0, sC = 0;   // batch strides in floats (0 broadcasts)
+  int transA = 0;                     // 0: A[m][k] ; 1: stored A[k][m]
+  int transB = 0;                     // 0: B[k][n] ; 1: stored B[n][k]
+  const float* kscale = nullptr;      // optional [batch][K]: B rows scaled by kscale[k]
+  long long sK = 0;
+  const float* meanA = nullptr;       // optional centring (covariance): A elem -= meanA[m]
+  const float* meanB = nullptr;       //                                 B elem -= meanB[n]
+  long long sMean = 0;
+  float alpha = 1.f;                  // C = alpha * (acc + E1)
+  const float* E1 = nullptr;
+  long long sE1 = 0;
+  int lde1 = 0;
+};
+int launch_gemm(const GemmArgs& g, int batch, cudaStream_t st);
+
+// ---- elementwise / reductions ---------------------------------------------------------------
+int elem_blocks_per_graph(int D);
+int rho_param_count(int H);
+
+int launch_lambda_step(int k, const float* params, int H, float lambda_init, int B_total,
+                       const float* normf, float* lam, float* lamfeat, cudaStream_t st);
+int launch_z_update_fwd(const float* X, const float* S, const float* Tprev, const float* params,
+                        int H, int B, int D, float* Z, float* part, float* normf_out,
+                        unsigned* counter, cudaStream_t st);
+int launch_z_update_bwd(const float* GZ, const float* X, const float* S, const float* Tprev,
+                        const float* params, int H, int B, int D, float* GX, float* GF3,
+                        float* rho_part, cudaStream_t st);
+int launch_phi(float* Gt, const float* beta, const float* sroot, const float* snorm,
+               const float* lam, int exact_sqrt, int B, int D, float* trh_part, cudaStream_t st);
+int launch_gb_finish(const float* Gb, const float* GF3, const float* S, int B, int D, float* Gnext,
+                     float* sgb_part, cudaStream_t st);
+int launch_init_f(const float* wS, const float* params, int B, int D, float* f0, cudaStream_t st);
+int launch_theta_init_diag(const float* S, const float* params, int B, int D, float* theta0,
+                           cudaStream_t st);
+int launch_dot_partial(const float* A, const float* Bm, int B, int D, int diag_sq, float* part,
+                       cudaStream_t st);
+int launch_finalize_grads(const float* params, int H, int L, int nblk, const float* rho_part,
+                          const float* trh_part, const float* sgb_part, const float* t0_part,
+                          const float* lam, const float* lamfeat, float* grad_params,
+                          cudaStream_t st);
+int launch_loss_terms(const float* theta, const float* S, long long strideS, const float* logdet,
+                      int B, int D, float Bdiv, float* lossb, float* loss_out, unsigned* counter,
+                      cudaStream_t st);
+int launch_colmean(const float* X, int B, int M, int D, float* mean, cudaStream_t st);
+int launch_condition(float* S, float* wS, int B, int D, float offset, cudaStream_t st);
+
+}  // namespace uglad

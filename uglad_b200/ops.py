@@ -1,0 +1,199 @@
+"""torch-facing wrappers of the C-ABI: tensors in, tensors out, autograd where the reference
+has it.  PyTorch supplies device memory, streams and torch.distributed; every floating-point
+operation of the hot path runs in libuglad_b200.so."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import UgladDims, check
+
+
+def _stream(t: torch.Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.UgladError(f"{name} must be a CUDA tensor (uglad_b200 has no CPU path)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def covariance(X: torch.Tensor) -> torch.Tensor:
+    """S[b] = (X_b - mean)^T (X_b - mean) / M for X [B,M,D] (prepare_data.py:342-344)."""
+    X = _f32c(X, "X")
+    if X.dim() == 2:
+        X = X.unsqueeze(0)
+    B, M, D = X.shape
+    S = torch.empty(B, D, D, device=X.device, dtype=torch.float32)
+    mean = torch.empty(B, D, device=X.device, dtype=torch.float32)
+    check(_lib.load().uglad_covariance(_ptr(X), B, M, D, _ptr(S), _ptr(mean), _stream(X)), "uglad_covariance")
+    return S
+
+
+def eigh(A: torch.Tensor, indefinite: bool = True) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Batched symmetric eigendecomposition.  Returns (w [B,D], Vt [B,D,D] rows = vectors,
+    info [B,4] = sweeps, shift, trace, sum(w))."""
+    A = _f32c(A, "A")
+    B, D, _ = A.shape
+    lib = _lib.load()
+    w = torch.empty(B, D, device=A.device, dtype=torch.float32)
+    Vt = torch.empty(B, D, D, device=A.device, dtype=torch.float32)
+    info = torch.empty(B, 4, device=A.device, dtype=torch.float32)
+    ns = lib.uglad_eigh_scratch_floats(B, D)
+    scratch = torch.empty(max(ns, 1), device=A.device, dtype=torch.float32)
+    check(lib.uglad_eigh(_ptr(A), B, D, 1 if indefinite else 0, _ptr(w), _ptr(Vt), _ptr(info),
+                         _ptr(scratch), _stream(A)), "uglad_eigh")
+    return w, Vt, info
+
+
+class ConditionedCovariance:
+    """S after the eigenvalue repair of prepare_data.py:345-355 plus its eigendecomposition,
+    which every forward reuses for theta_0 = (S + t I)^-1 (glad.py:115-117)."""
+
+    def __init__(self, S: torch.Tensor, offset: float = 0.1, repair: bool = True):
+        S = _f32c(S, "S").clone()
+        B, D, _ = S.shape
+        lib = _lib.load()
+        self.wS = torch.empty(B, D, device=S.device, dtype=torch.float32)
+        self.VtS = torch.empty(B, D, D, device=S.device, dtype=torch.float32)
+        self.info = torch.empty(B, 4, device=S.device, dtype=torch.float32)
+        ns = lib.uglad_eigh_scratch_floats(B, D)
+        scratch = torch.empty(max(ns, 1), device=S.device, dtype=torch.float32)
+        if repair:
+            check(lib.uglad_condition_covariance(_ptr(S), B, D, float(offset), _ptr(self.wS), _ptr(self.VtS),
+                                                 _ptr(self.info), _ptr(scratch), _stream(S)),
+                  "uglad_condition_covariance")
+        else:
+            check(lib.uglad_eigh(_ptr(S), B, D, 1, _ptr(self.wS), _ptr(self.VtS), _ptr(self.info),
+                                 _ptr(scratch), _stream(S)), "uglad_eigh")
+        self.S = S
+
+
+def _eig_of(S: torch.Tensor) -> ConditionedCovariance:
+    """Eigendecomposition of a covariance batch, cached ON the tensor object (keyed by its
+    version counter) so that the epochs of one fit, which pass the same Sb every time
+    (main.py:389-399), pay for it once and a recycled allocation can never alias it."""
+    hit = getattr(S, "_uglad_eig", None)
+    if hit is not None and hit[0] == S._version:
+        return hit[1]
+    cc = ConditionedCovariance(S, repair=False)
+    try:
+        S._uglad_eig = (S._version, cc)
+    except Exception:  # exotic tensor subclasses without attribute storage
+        pass
+    return cc
+
+
+def make_dims(B, D, L, H, init_diag, B_total=None, exact_sqrt=False, lambda_init=1.0) -> UgladDims:
+    return UgladDims(int(B), int(D), int(L), int(H), int(init_diag), int(B if B_total is None else B_total),
+                     int(bool(exact_sqrt)), float(lambda_init))
+
+
+class GladFunction(torch.autograd.Function):
+    """theta_pred = glad(S; params)  (glad.py:74-150) with the hand-written backward."""
+
+    @staticmethod
+    def forward(ctx, S, flat_params, L, init_diag, H, lambda_init, exact_sqrt, group):
+        lib = _lib.load()
+        S = _f32c(S, "Sb")
+        flat_params = _f32c(flat_params, "params")
+        B, D, _ = S.shape
+        world = 1
+        B_total = B
+        if group is not None:
+            import torch.distributed as dist
+            world = dist.get_world_size(group)
+            if world > 1:
+                cnt = torch.tensor([B], device=S.device, dtype=torch.int64)
+                dist.all_reduce(cnt, group=group)
+                B_total = int(cnt.item())
+        dims = make_dims(B, D, L, H, init_diag, B_total, exact_sqrt, lambda_init)
+        if flat_params.numel() != lib.uglad_param_count(H):
+            raise _lib.UgladError("packed parameter vector has the wrong length")
+        n = lib.uglad_workspace_floats(C.byref(dims))
+        if n == 0:
+            raise _lib.UgladError(lib.uglad_last_error().decode())
+        ws = torch.empty(n, device=S.device, dtype=torch.float32)
+        eig = _eig_of(S) if init_diag == 0 else None
+        wS, VtS = (eig.wS, eig.VtS) if eig is not None else (None, None)
+        st = _stream(S)
+        if world == 1:
+            check(lib.uglad_glad_forward(C.byref(dims), _ptr(S), _ptr(flat_params), _ptr(wS), _ptr(VtS),
+                                         _ptr(ws), st), "uglad_glad_forward")
+        else:
+            import torch.distributed as dist
+            check(lib.uglad_glad_init_forward(C.byref(dims), _ptr(S), _ptr(flat_params), _ptr(wS), _ptr(VtS),
+                                              _ptr(ws), st), "uglad_glad_init_forward")
+            off = lib.uglad_workspace_offset(C.byref(dims), b"normf")
+            normf = ws[off:off + L]
+            for k in range(L):
+                check(lib.uglad_glad_layer_forward(C.byref(dims), k, _ptr(S), _ptr(flat_params), _ptr(ws), st),
+                      "uglad_glad_layer_forward")
+                if k + 1 < L:  # the mean of glad.py:147 runs over every process's graphs
+                    dist.all_reduce(normf[k:k + 1], group=group)
+        off = lib.uglad_workspace_offset(C.byref(dims), b"theta")
+        theta = ws[off:off + B * D * D].view(B, D, D)
+        ctx.dims, ctx.ws, ctx.S, ctx.params, ctx.eig, ctx.group, ctx.world = dims, ws, S, flat_params, eig, group, world
+        return theta
+
+    @staticmethod
+    def backward(ctx, grad_theta):
+        lib = _lib.load()
+        dims = ctx.dims
+        g = _f32c(grad_theta, "grad_theta")
+        gp = torch.empty(ctx.params.numel(), device=g.device, dtype=torch.float32)
+        wS, VtS = (ctx.eig.wS, ctx.eig.VtS) if ctx.eig is not None else (None, None)
+        check(lib.uglad_glad_backward(C.byref(dims), _ptr(ctx.S), _ptr(ctx.params), _ptr(wS), _ptr(VtS),
+                                      _ptr(ctx.ws), _ptr(g), _ptr(gp), _stream(g)), "uglad_glad_backward")
+        if ctx.world > 1:  # the one collective of the data path: shared MLP gradients
+            import torch.distributed as dist
+            dist.all_reduce(gp, group=ctx.group)
+        return None, gp, None, None, None, None, None, None
+
+
+class GlassoLossFunction(torch.autograd.Function):
+    """loss = sum_b(-logdet theta_b + <S_b, theta_b>) / Bdiv  (main.py:306-315)."""
+
+    @staticmethod
+    def forward(ctx, theta, S, Bdiv):
+        lib = _lib.load()
+        theta = _f32c(theta, "theta")
+        S = _f32c(S, "S")
+        B, D, _ = theta.shape
+        sb = S.shape[0]
+        loss = torch.empty(1, device=theta.device, dtype=torch.float32)
+        need_grad = ctx.needs_input_grad[0]
+        grad = torch.empty_like(theta) if need_grad else None
+        scratch = torch.empty(lib.uglad_loss_scratch_floats(B, D), device=theta.device, dtype=torch.float32)
+        check(lib.uglad_glasso_loss(_ptr(theta), _ptr(S), B, D, sb, float(Bdiv), _ptr(loss), _ptr(grad),
+                                    _ptr(scratch), _stream(theta)), "uglad_glasso_loss")
+        ctx.grad = grad
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, gout):
+        return ctx.grad * gout, None, None
+
+
+def z_update(X, S, theta_prev, flat_params, H=3):
+    """Entrywise soft threshold with the rho_l1 MLP (glad_params.py:56-77); returns
+    (Z, sum ||Z-X||_F^2 over the batch)."""
+    lib = _lib.load()
+    X, S, theta_prev, flat_params = (_f32c(t, "arg") for t in (X, S, theta_prev, flat_params))
+    B, D, _ = X.shape
+    Z = torch.empty_like(X)
+    normf = torch.empty(1, device=X.device, dtype=torch.float32)
+    scratch = torch.empty(64 * B + 16, device=X.device, dtype=torch.float32)
+    check(lib.uglad_z_update(_ptr(X), _ptr(S), _ptr(theta_prev), _ptr(flat_params), H, B, D, _ptr(Z),
+                             _ptr(normf), _ptr(scratch), _stream(X)), "uglad_z_update")
+    return Z, normf
