@@ -77,10 +77,15 @@ int uglad_glad_init_forward(const uglad_dims* d, const float* S, const float* pa
  * all-reduced over processes when B_total > B) to form lambda_k, then runs the theta update,
  * the Z update and leaves the local sum of ||Z-X||_F^2 in normf[k].                        */
 int uglad_glad_layer_forward(const uglad_dims* d, int k, const float* S, const float* params,
-                             float* ws, void* stream);
-/* glad.py:74-150 in one call (single process: B_total == B). */
+                             float* ws, const float* warm_ws, void* stream);
+/* glad.py:74-150 in one call (single process: B_total == B).
+ * warm_ws (may be NULL): the workspace of an earlier forward with the SAME dims -- normally the
+ * previous epoch's.  Its per-layer eigenvectors seed the Jacobi solver (the matrices differ by
+ * one optimiser step, so ~2 sweeps replace ~9).  It only changes the work done, never the
+ * converged result; any stale or unrelated workspace is a valid (if useless) seed. */
 int uglad_glad_forward(const uglad_dims* d, const float* S, const float* params,
-                       const float* wS, const float* VtS, float* ws, void* stream);
+                       const float* wS, const float* VtS, float* ws, const float* warm_ws,
+                       void* stream);
 /* backward of the above: grad_theta[B][D][D] -> grad_params[uglad_param_count(H)] (local
  * contribution; the caller all-reduces it over processes).                               */
 int uglad_glad_backward(const uglad_dims* d, const float* S, const float* params,
@@ -93,6 +98,17 @@ int uglad_glad_backward(const uglad_dims* d, const float* S, const float* params
 size_t uglad_loss_scratch_floats(int B, int D);
 int uglad_glasso_loss(const float* theta, const float* S, int B, int D, int S_batch, float Bdiv,
                       float* loss_out, float* grad_theta, float* scratch, void* stream);
+
+/* instrumentation for bench.py: kernels launched by this library since it was loaded, and
+ * CUDA-event timing of the dominant kernel (the Jacobi eigensolver): uglad_profile(enable, ..)
+ * returns the time and launch count accumulated since the previous call, then switches the
+ * event brackets on or off.                                                               */
+unsigned long long uglad_launch_count(void);
+int uglad_profile(int enable, double* total_ms, unsigned long long* launches);
+
+/* developer knobs used by the tuning scripts: "eig_lp" (lanes per column pair, 0 = auto),
+ * "eig_keepg" (-1 auto / 0 / 1: keep A + sigma I in a second shared-memory buffer).        */
+int uglad_tune(const char* key, int value);
 
 /* building blocks exported for the parity tests */
 int uglad_z_update(const float* X, const float* S, const float* theta_prev, const float* params,

@@ -1,0 +1,263 @@
+"""Parity of the CUDA path (through the C-ABI library) against the oracle and the golden
+vectors produced by the real reference.  Run on the B200 box:  pytest -m gpu
+
+Tolerances (BASELINE.json north_star): theta within 1e-4 relative Frobenius error of the
+reference's torch result; recovered edge set identical except for entries within 1e-5 of the
+threshold.  Gradients / losses are held to 1e-3 / 1e-4 relative."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import uglad_oracle as O  # the checker, never the thing under test
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CASES = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")))
+THETA_TOL = 1e-4
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def load_model(g, tag):
+    from uglad_b200.glad.glad_params import GladParams
+    model = GladParams(1.0, 3, 3)
+    model.load_state_dict({k: torch.tensor(g[f"{tag}/{k}"]) for k in O.PARAM_KEYS})
+    return model
+
+
+def edge_sets_match(theta, ref, margin=1e-5):
+    """Supports must agree wherever the reference entry is not within `margin` of zero."""
+    clear = np.abs(ref) > margin
+    same = (theta != 0) == (ref != 0)
+    return bool(np.all(same | ~clear)) and bool(np.all(np.abs(theta[(ref == 0)]) <= margin))
+
+
+def test_library_is_the_cuda_one():
+    from uglad_b200 import _lib
+    lib = _lib.load()
+    assert lib.uglad_abi_version() == 1
+    assert os.path.basename(_lib.LIB_PATH) == "libuglad_b200.so"
+
+
+@pytest.mark.parametrize("D,B", [(1, 2), (2, 3), (3, 2), (10, 4), (33, 3), (100, 5), (129, 2), (167, 2), (200, 2), (232, 1)])
+def test_eigh_indefinite(dev, D, B):
+    from uglad_b200 import ops
+    rng = np.random.default_rng(D)
+    A = rng.standard_normal((B, D, D))
+    A = (A + A.transpose(0, 2, 1)) / 2
+    w, Vt, info = ops.eigh(torch.tensor(A, dtype=torch.float32, device=dev), indefinite=True)
+    w, Vt = w.cpu().numpy().astype(np.float64), Vt.cpu().numpy().astype(np.float64)
+    R = np.einsum("bki,bk,bkj->bij", Vt, w, Vt)
+    assert rel(R, A) < 3e-5
+    assert np.abs(np.einsum("bki,bli->bkl", Vt, Vt) - np.eye(D)).max() < 2e-5
+    assert np.abs(np.sort(w, 1) - np.linalg.eigvalsh(A)).max() < 3e-5 * np.abs(A).sum(-1).max()
+
+
+@pytest.mark.parametrize("D", [5, 64, 150])
+def test_eigh_positive_definite_and_degenerate(dev, D):
+    from uglad_b200 import ops
+    rng = np.random.default_rng(D)
+    Q, _ = np.linalg.qr(rng.standard_normal((D, D)))
+    ev = np.concatenate([np.full(D // 2, 2.0), np.linspace(0.05, 5.0, D - D // 2)])  # repeated eigenvalue
+    A = (Q * ev) @ Q.T
+    w, Vt, _ = ops.eigh(torch.tensor(A[None], dtype=torch.float32, device=dev), indefinite=False)
+    w, Vt = w.cpu().numpy().astype(np.float64), Vt.cpu().numpy().astype(np.float64)
+    assert np.abs(np.sort(w[0]) - np.sort(ev)).max() < 2e-5
+    assert rel(np.einsum("bki,bk,bkj->bij", Vt, w, Vt)[0], A) < 2e-5
+
+
+def test_eigh_diagonal_and_zero_offdiag(dev):
+    from uglad_b200 import ops
+    d = np.array([3.0, -1.0, 0.5, 7.0, 2.0, 2.0])
+    w, Vt, _ = ops.eigh(torch.tensor(np.diag(d)[None], dtype=torch.float32, device=dev), indefinite=True)
+    assert np.abs(np.sort(w.cpu().numpy()[0]) - np.sort(d)).max() < 1e-5
+
+
+@pytest.mark.parametrize("B,M,D", [(1, 3, 2), (2, 50, 7), (3, 500, 20), (1, 1000, 100), (2, 257, 65)])
+def test_covariance(dev, B, M, D):
+    from uglad_b200 import ops
+    rng = np.random.default_rng(M)
+    X = rng.random((B, M, D))
+    S = ops.covariance(torch.tensor(X, dtype=torch.float32, device=dev)).cpu().numpy()
+    assert rel(S, O.covariance(X, offset=0.1)) < 5e-6
+
+
+def test_rank_deficient_covariance_is_repaired(dev):
+    from uglad_b200.utils import prepare_data
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((1, 5, 12))  # fewer samples than features
+    S = prepare_data.get_covariance(X, offset=0.1).cpu().numpy()
+    assert rel(S, O.covariance(X, offset=0.1)) < 1e-5
+    assert abs(np.linalg.eigvalsh(S[0].astype(np.float64)).min() - 0.1) < 1e-5
+
+
+def test_ragged_sample_counts(dev):
+    from uglad_b200.utils import prepare_data
+    rng = np.random.default_rng(4)
+    Xs = [rng.random((m, 9)) for m in (40, 55, 40)]
+    S = prepare_data.get_covariance(Xs).cpu().numpy()
+    for i, X in enumerate(Xs):
+        assert rel(S[i], O.covariance([X])[0]) < 5e-6
+
+
+def test_z_update_matches_oracle(dev):
+    from uglad_b200 import ops
+    P = O.init_params(5)
+    rng = np.random.default_rng(5)
+    X, S, T = (torch.tensor(rng.standard_normal((3, 17, 17)), dtype=torch.float32) for _ in range(3))
+    flat = torch.cat([P[k].detach().reshape(-1) for k in O.PARAM_KEYS]).to(dev)
+    Z, normf = ops.z_update(X.to(dev), S.to(dev), T.to(dev), flat, 3)
+    Zo = O.eta_threshold(P, X, S, T).detach()
+    assert rel(Z.cpu().numpy(), Zo.numpy()) < 1e-6
+    assert abs(normf.item() - float(((Zo - X) ** 2).sum())) < 1e-4 * float(((Zo - X) ** 2).sum())
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
+def test_forward_backward_against_reference_golden(dev, path):
+    from uglad_b200 import main as ug, ops
+    ops.reset_warm_start()
+    g = np.load(path)
+    L, idg = int(g["L"]), int(g["init_diag"])
+    S = torch.tensor(g["S"], device=dev)
+    model = load_model(g, "p0")
+    theta, loss = ug.forward_uGLAD(S, model, L=L, INIT_DIAG=idg)
+    loss.backward()
+    th = theta.detach().cpu().numpy()
+    assert rel(th, g["theta0"]) < THETA_TOL
+    assert edge_sets_match(th, g["theta0"])
+    assert abs(loss.item() - float(g["loss0"])) < 1e-4 * max(1.0, abs(float(g["loss0"])))
+    for k, p in model.named_parameters():
+        assert rel(p.grad.cpu().numpy(), g["g0/" + k]) < 1e-3, k
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
+def test_training_loop_against_reference_golden(dev, path):
+    """Same seeds, same Adam loop (main.py:389-414): the trajectory of the real reference."""
+    from uglad_b200 import main as ug, ops
+    ops.reset_warm_start()
+    g = np.load(path)
+    L, idg, E = int(g["L"]), int(g["init_diag"]), int(g["epochs"])
+    S = torch.tensor(g["S"], device=dev)
+    model = load_model(g, "p0")
+    opt = ug.glad.get_optimizers(model, lr_glad=float(g["lr"]))
+    theta, losses = ug._fit_loop(S, model, opt, E, L, idg, False)
+    losses = torch.stack(losses).cpu().numpy()
+    assert np.abs(losses - g["losses"]).max() < 2e-4 * max(1.0, np.abs(g["losses"]).max())
+    th = theta.detach().cpu().numpy()
+    assert rel(th, g["thetaT"]) < THETA_TOL
+    assert edge_sets_match(th, g["thetaT"])
+    if "consensus" in g.files:
+        c = ug.get_final_precision_from_batch(theta.detach(), type="min").cpu().numpy()
+        assert rel(c, g["consensus"]) < THETA_TOL
+
+
+def test_warm_start_does_not_change_the_result(dev):
+    from uglad_b200 import main as ug, ops
+    g = np.load(CASES[0])
+    S = torch.tensor(g["S"], device=dev)
+    model = load_model(g, "p0")
+    ops.reset_warm_start()
+    with torch.no_grad():
+        cold = ug.glad.glad(S, model, L=int(g["L"]), INIT_DIAG=int(g["init_diag"])).clone()
+        warm = ug.glad.glad(S, model, L=int(g["L"]), INIT_DIAG=int(g["init_diag"])).clone()
+    assert rel(warm.cpu().numpy(), cold.cpu().numpy()) < 2e-5
+
+
+def test_oracle_parity_random_params_and_exact_sqrt(dev):
+    """Fresh seeds (not the golden ones), B > 1, both square-root modes, float64 spectral oracle."""
+    from uglad_b200 import main as ug, ops
+    from uglad_b200.glad.glad_params import GladParams
+    rng = np.random.default_rng(21)
+    X = rng.random((4, 80, 12))
+    S64 = O.covariance(X)
+    S = torch.tensor(S64, dtype=torch.float32, device=dev)
+    P = O.init_params(21)
+    model = GladParams(1.0, 3, 3)
+    model.load_state_dict({k: v.detach() for k, v in P.items()})
+    for exact in (False, True):
+        ops.reset_warm_start()
+        r = O.spectral_forward_backward(S.cpu().numpy(), P, L=9, init_diag=0, exact_sqrt=exact)
+        model.zero_grad()
+        theta = ug.glad.glad(S, model, L=9, exact_sqrt=exact)
+        loss = ug.loss_uGLAD(theta, S)
+        loss.backward()
+        assert rel(theta.detach().cpu().numpy(), r["theta"]) < 2e-5
+        assert abs(loss.item() - r["loss"]) < 1e-4 * max(1.0, abs(r["loss"]))
+        for k, p in model.named_parameters():
+            assert rel(p.grad.cpu().numpy(), r["grads"][k]) < 1e-3, (exact, k)
+
+
+def test_consensus_mode_loss_broadcasts_full_covariance(dev):
+    """main.py:620-622: K sub-sampled covariances in, the full-data covariance in the loss."""
+    from uglad_b200 import main as ug, ops
+    ops.reset_warm_start()
+    rng = np.random.default_rng(8)
+    X = rng.random((1, 90, 10))
+    Sfull = torch.tensor(O.covariance(X), dtype=torch.float32)
+    SK = torch.tensor(O.covariance([X[0][:60], X[0][30:], X[0][::2]]), dtype=torch.float32)
+    P = O.init_params(8)
+    from uglad_b200.glad.glad_params import GladParams
+    model = GladParams(1.0, 3, 3)
+    model.load_state_dict({k: v.detach() for k, v in P.items()})
+    th_o, loss_o = O.forward_loss(SK, P, 15, 0, loss_S=Sfull)
+    loss_o.backward()
+    th, loss = ug.forward_uGLAD(SK.to(dev), model, L=15, loss_Sb=Sfull.to(dev))
+    loss.backward()
+    assert rel(th.detach().cpu().numpy(), th_o.detach().numpy()) < THETA_TOL
+    assert abs(loss.item() - loss_o.item()) < 1e-4 * max(1.0, abs(loss_o.item()))
+    for k, p in model.named_parameters():
+        assert rel(p.grad.cpu().numpy(), P[k].grad.numpy()) < 1e-3, k
+
+
+def test_indefinite_theta_gives_nan_loss_like_torch_logdet(dev):
+    from uglad_b200 import main as ug
+    theta = torch.tensor(np.diag([1.0, -2.0, 3.0])[None], dtype=torch.float32, device=dev)
+    S = torch.eye(3, device=dev)[None]
+    assert torch.isnan(ug.loss_uGLAD(theta, S))
+    assert torch.isnan(O.glasso_loss(theta.cpu(), S.cpu()))
+
+
+def test_fit_api_direct_mode(dev):
+    """uGLAD_GL.fit keeps the sklearn-style outputs (main.py:34-151)."""
+    from uglad_b200 import main as ug
+    from uglad_b200.utils import prepare_data
+    rng = np.random.default_rng(9)
+    Xb, theta_true = prepare_data.get_data(10, [0.2, 0.2], 300, batch_size=1, eig_offset=1.0, rng=rng)
+    m = ug.uGLAD_GL()
+    m.fit(Xb[0], centered=False, epochs=5, lr=0.002, L=15, verbose=False, mode="direct")
+    assert m.precision_.shape == (10, 10) and m.covariance_.shape == (10, 10) and m.location_.shape == (10,)
+    assert np.isfinite(m.precision_).all()
+    assert len(m.node_names_) == 10
+
+
+def test_size_independent_properties_at_full_size(dev):
+    """BASELINE configs[2] shape (D=100, many graphs): properties that need no oracle run --
+    theta symmetric, permutation of the batch permutes the output."""
+    from uglad_b200 import main as ug, ops
+    from uglad_b200.utils import prepare_data
+    rng = np.random.default_rng(10)
+    Xb, _ = prepare_data.get_data(100, [0.05, 0.05], 300, batch_size=16, eig_offset=1.0, rng=rng)
+    S = prepare_data.get_covariance(Xb)
+    torch.manual_seed(0)
+    model, _ = ug.init_uGLAD(lr=0.002)
+    ops.reset_warm_start()
+    with torch.no_grad():
+        th = ug.glad.glad(S, model, L=15).clone()
+        perm = torch.randperm(16, device=dev)
+        ops.reset_warm_start()
+        th_p = ug.glad.glad(S[perm].contiguous(), model, L=15).clone()
+    assert rel(th.cpu().numpy(), th.transpose(1, 2).cpu().numpy()) < 1e-5
+    assert rel(th_p.cpu().numpy(), th[perm].cpu().numpy()) < 1e-5

@@ -32,11 +32,14 @@ SIGNATURES = {
     "uglad_workspace_floats": (_Z, [_DP]),
     "uglad_workspace_offset": (_Z, [_DP, C.c_char_p]),
     "uglad_glad_init_forward": (_I, [_DP, _P, _P, _P, _P, _P, _P]),
-    "uglad_glad_layer_forward": (_I, [_DP, _I, _P, _P, _P, _P]),
-    "uglad_glad_forward": (_I, [_DP, _P, _P, _P, _P, _P, _P]),
+    "uglad_glad_layer_forward": (_I, [_DP, _I, _P, _P, _P, _P, _P]),
+    "uglad_glad_forward": (_I, [_DP, _P, _P, _P, _P, _P, _P, _P]),
     "uglad_glad_backward": (_I, [_DP, _P, _P, _P, _P, _P, _P, _P, _P]),
     "uglad_loss_scratch_floats": (_Z, [_I, _I]),
     "uglad_glasso_loss": (_I, [_P, _P, _I, _I, _I, _F, _P, _P, _P, _P]),
+    "uglad_launch_count": (C.c_ulonglong, []),
+    "uglad_profile": (_I, [_I, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),
+    "uglad_tune": (_I, [C.c_char_p, _I]),
     "uglad_z_update": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
 }
 

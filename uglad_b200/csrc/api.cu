@@ -4,6 +4,10 @@
 //   prepare_data.py:328-356 -> uglad_covariance + uglad_condition_covariance
 #include <stdarg.h>
 #include <string.h>
+#include <atomic>
+#include <mutex>
+#include <utility>
+#include <vector>
 #include "kernels.cuh"
 
 namespace uglad {
@@ -14,6 +18,28 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// CUDA-event brackets around the dominant kernel, switched on by uglad_profile(1)
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+void profile_begin(cudaStream_t st) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  cudaEventRecord(a, st);
+  g_prof_events.emplace_back(a, b);
+}
+void profile_end(cudaStream_t st) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof_events.empty()) cudaEventRecord(g_prof_events.back().second, st);
 }
 
 static inline size_t al4(size_t x) { return (x + 3) & ~(size_t)3; }
@@ -180,7 +206,7 @@ int uglad_glad_init_forward(const uglad_dims* d, const float* S, const float* pa
 }
 
 int uglad_glad_layer_forward(const uglad_dims* d, int k, const float* S, const float* params,
-                             float* ws, void* stream) {
+                             float* ws, const float* warm_ws, void* stream) {
   if (check_dims(d)) return 1;
   if (k < 0 || k >= d->L) { set_error("glad_layer_forward: k=%d outside [0,%d)", k, d->L); return 1; }
   cudaStream_t st = (cudaStream_t)stream;
@@ -198,6 +224,7 @@ int uglad_glad_layer_forward(const uglad_dims* d, int k, const float* S, const f
   a.w = ws + w.beta + (size_t)k * w.n1; a.Vt = Vk; a.info = ws + w.info + (size_t)k * B * 4;
   a.f = fk; a.sroot = ws + w.sroot + (size_t)k * w.n1; a.snorm = ws + w.snorm + (size_t)k * B;
   a.scratch = ws + w.eig_scratch;
+  a.warmVt = warm_ws ? warm_ws + w.Vt + (size_t)k * w.n2 : nullptr;
   a.D = D; a.shift_mode = 1; a.tail = TAIL_LAYER; a.exact_sqrt = d->exact_sqrt;
   if (launch_eig(a, B, st)) return 1;
   if (spectral_recon(Vk, fk, Xk, B, D, 1.f, nullptr, 0, st)) return 1;
@@ -206,12 +233,13 @@ int uglad_glad_layer_forward(const uglad_dims* d, int k, const float* S, const f
 }
 
 int uglad_glad_forward(const uglad_dims* d, const float* S, const float* params,
-                       const float* wS, const float* VtS, float* ws, void* stream) {
+                       const float* wS, const float* VtS, float* ws, const float* warm_ws,
+                       void* stream) {
   if (check_dims(d)) return 1;
   if (d->B_total != d->B) { set_error("glad_forward: B_total != B; drive the layers from the host and all-reduce normf"); return 1; }
   if (uglad_glad_init_forward(d, S, params, wS, VtS, ws, stream)) return 1;
   for (int k = 0; k < d->L; ++k)
-    if (uglad_glad_layer_forward(d, k, S, params, ws, stream)) return 1;
+    if (uglad_glad_layer_forward(d, k, S, params, ws, warm_ws, stream)) return 1;
   return 0;
 }
 
@@ -287,6 +315,33 @@ int uglad_glasso_loss(const float* theta, const float* S, int B, int D, int S_ba
                         reinterpret_cast<unsigned*>(counter), st)) return 1;
   if (grad_theta) return spectral_recon(Vt, f, grad_theta, B, D, 1.0f / Bdiv, S, sS, st);
   return 0;
+}
+
+unsigned long long uglad_launch_count(void) { return g_launches.load(); }
+
+int uglad_profile(int enable, double* total_ms, unsigned long long* launches) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double tot = 0.0;
+  unsigned long long n = 0;
+  for (auto& e : g_prof_events) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(e.second) == cudaSuccess && cudaEventElapsedTime(&ms, e.first, e.second) == cudaSuccess) {
+      tot += ms;
+      ++n;
+    }
+    cudaEventDestroy(e.first);
+    cudaEventDestroy(e.second);
+  }
+  g_prof_events.clear();
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = n;
+  g_prof_on = enable != 0;
+  return 0;
+}
+
+int uglad_tune(const char* key, int value) {
+  if (!key) return 1;
+  return eig_small_tune(key, value);
 }
 
 int uglad_z_update(const float* X, const float* S, const float* theta_prev, const float* params,

@@ -10,6 +10,7 @@
 namespace uglad {
 
 void set_error(const char* fmt, ...);
+void count_launch();  // every kernel launch of the library is counted (uglad_launch_count)
 
 #define UGLAD_CHECK_LAUNCH(name)                                                      \
   do {                                                                                \
@@ -18,6 +19,7 @@ void set_error(const char* fmt, ...);
       uglad::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));       \
       return 1;                                                                       \
     }                                                                                 \
+    uglad::count_launch();                                                            \
   } while (0)
 
 #define UGLAD_CUDA(call)                                                              \

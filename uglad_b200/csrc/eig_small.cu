@@ -5,13 +5,34 @@
 // such as b = S/lambda - theta of glad.py:139), orthogonalising the columns of U gives
 // U -> V diag(lambda + sigma): eigenvalues are column norms minus sigma, eigenvectors the
 // normalised columns, so ONE D x D matrix in shared memory is the whole state (D <= 232
-// fits the 227 KB of a B200 SM).  A warp owns a column pair per step of a round-robin
-// tournament; the three dot products are warp-shuffle reductions; one __syncthreads per
-// round.  The tail turns eigenvalues into what the caller needs:
+// fits the 227 KB of a B200 SM).
+//
+// Mapping: a group of LP lanes (8/16/32) owns one column pair per step of a round-robin
+// tournament, each lane holding CH float4 chunks of both columns in registers, so a round
+// is (nearly always) a single pass; the only reduction per pair is the dot product
+// (column norms are cached and updated analytically, refreshed every sweep); the rotation
+// is computed with MUFU rsqrt/rcp + one Newton step and applied in the small-angle-accurate
+// form a' = a - s(b + tau a), b' = b + s(a - tau b), whose rounding error scales with the
+// rotation, not with the column (late sweeps add almost no error).  One __syncthreads per
+// round.
+//
+// sigma: 1.35 x a 10-step power-iteration estimate of ||A||_2; the result is validated
+// by sum(norms) == trace + D sigma and redone with the guaranteed min(Gershgorin,
+// Frobenius) bound if that fails.  A tight sigma matters: eigenvalue error ~ eps (|A|+sigma).
+//
+// When two D x D buffers fit (D <= 166) the unshifted-then-shifted input G is kept beside U:
+//   * warm start: U_0 = G V_prev (V_prev = the same layer's eigenvectors from the previous
+//     epoch, whose b differs by one Adam step) is already nearly orthogonal, so ~2 sweeps
+//     replace ~9;
+//   * eigenvalues are Rayleigh quotients v^T G v of the final vectors (second-order
+//     accurate) instead of accumulated column norms.
+//
+// Tails:
 //   TAIL_LAYER: f_k = (s_k - beta_k)/2 with s_k the reference's 10-step Newton-Schulz
 //               square root of beta_k^2 + 4/lambda collapsed onto the eigenvalues
 //               (torch_sqrtm.py:12-28, glad.py:140-142);
 //   TAIL_LOSS : logdet and -1/eig for main.py:307 (torch.logdet) and its gradient.
+#include <string.h>
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -30,14 +51,57 @@ __device__ __forceinline__ void rr_pair(int n, int r, int i, int& p, int& q) {
   }
 }
 
-template <int CH>
-__global__ void __launch_bounds__(1024, 1) eig_jacobi_small_kernel(EigArgs a) {
+template <int LP>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
+}
+
+// t = G u for one column u of U (both in shared memory); lane `gl` of the group keeps the
+// float4 chunks gl, gl+LP, ... of t in registers.
+template <int LP, int CH>
+__device__ __forceinline__ void group_matvec(const float* __restrict__ G, const float* __restrict__ u,
+                                             int D, int ld, int nch, int gl, float4* tv) {
+#pragma unroll
+  for (int c = 0; c < CH; ++c) tv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+  for (int j = 0; j < D; ++j) {
+    const float vj = u[j];
+    const float* gj = G + (size_t)j * ld;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int ch = gl + LP * c;
+      if (ch < nch) {
+        const float4 g4 = *reinterpret_cast<const float4*>(gj + 4 * ch);
+        tv[c].x = fmaf(g4.x, vj, tv[c].x);
+        tv[c].y = fmaf(g4.y, vj, tv[c].y);
+        tv[c].z = fmaf(g4.z, vj, tv[c].z);
+        tv[c].w = fmaf(g4.w, vj, tv[c].w);
+      }
+    }
+  }
+}
+
+constexpr int eig_max_threads(int LP, int CH) {
+  const int want = (116 * LP + 31) / 32 * 32, cap = (CH >= 8) ? 512 : 1024;  // CH=8 needs >64 registers
+  return want > cap ? cap : want;
+}
+
+template <int LP, int CH>
+__global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_kernel(EigArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int D = a.D, ld = a.ld;
   float* U = smem;                                // [D][ld] column-major
-  float* wv = U + (size_t)ld * D;                 // [ld] eigenvalues
-  double* redd = reinterpret_cast<double*>(wv + ld + (ld & 1));  // [32] reduction scratch
-  float* red = reinterpret_cast<float*>(redd + 32);              // [32]
+  float* Gk = a.keepG ? U + (size_t)ld * D : U;   // [D][ld] A + sigma I (kept) or alias of U
+  float* wv = Gk + (size_t)ld * D;                // [ld] eigenvalues / power-iteration x
+  float* nrm2 = wv + ld;                          // [ld] cached squared column norms / y
+  double* redd = reinterpret_cast<double*>(nrm2 + ld);  // [32]
+  float* red = reinterpret_cast<float*>(redd + 32);     // [32]
   __shared__ unsigned s_flag;
   __shared__ float s_sigma;
 
@@ -45,147 +109,271 @@ __global__ void __launch_bounds__(1024, 1) eig_jacobi_small_kernel(EigArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nthreads = blockDim.x, nwarps = nthreads >> 5;
   const int nch = ld >> 2;
+  const int grp = tid / LP, gl = tid % LP, ngroups = nthreads / LP;
+  const int n = D + (D & 1), npairs = n >> 1, m = n - 1;
+  const float tol = a.tol;
 
-  // ---- load (coalesced along the contiguous global dimension) ---------------------------
-  float trace_part = 0.f, fro_part = 0.f;
-  {
-    const size_t base = (size_t)b * D * D;
-    float inv_lam = 0.f;
-    const float* Sb = nullptr;
-    const float* Tb = nullptr;
-    const float* Ab = nullptr;
-    if (a.build) {
-      inv_lam = 1.0f / a.lam[0];
-      Sb = a.S + (size_t)b * a.strideS;
-      Tb = a.Theta + base;
-    } else {
-      Ab = a.A + base;
-    }
+  const size_t base = (size_t)b * D * D;
+  float inv_lam = 0.f;
+  const float* Sb = nullptr;
+  const float* Tb = nullptr;
+  const float* Ab = nullptr;
+  if (a.build) {
+    inv_lam = 1.0f / a.lam[0];
+    Sb = a.S + (size_t)b * a.strideS;
+    Tb = a.Theta + base;
+  } else {
+    Ab = a.A + base;
+  }
+
+  int sweeps = 0;
+  float sigma = 0.f, trace = 0.f, wsum = 0.f;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    // ---- load (coalesced along the contiguous global dimension) -------------------------
+    float trace_part = 0.f, fro_part = 0.f;
     for (int idx = tid; idx < D * ld; idx += nthreads) {
       const int col = idx / ld, row = idx - col * ld;
       float v = 0.f;
       if (row < D) {
         const size_t g = (size_t)col * D + row;
         v = a.build ? (inv_lam * Sb[g] - Tb[g]) : Ab[g];
-        fro_part += v * v;
+        fro_part = fmaf(v, v, fro_part);
         if (row == col) trace_part += v;
       }
-      U[idx] = v;
+      Gk[idx] = v;
     }
-  }
-  if (tid == 0) s_flag = 0u;
-  const float trace = block_sum(trace_part, red);
-  const float fro = sqrtf(block_sum(fro_part, red));
-  // Gershgorin: max column abs-sum (symmetric input)
-  float gmax = 0.f;
-  for (int col = warp; col < D; col += nwarps) {
-    float s = 0.f;
-    for (int r = lane; r < D; r += 32) s += fabsf(U[(size_t)col * ld + r]);
-    s = warp_sum(s);
-    gmax = fmaxf(gmax, s);
-  }
-  gmax = block_max(gmax, red);
-  if (tid == 0) {
-    float sg = 0.f;
+    if (tid == 0) s_flag = 0u;
+    trace = block_sum(trace_part, red);
     if (a.shift_mode == 1) {
-      const float bound = fminf(gmax, fro);
-      sg = (bound > 0.f) ? 1.25f * bound : 1.0f;
-    }
-    s_sigma = sg;
-  }
-  __syncthreads();
-  const float sigma = s_sigma;
-  if (sigma != 0.f)
-    for (int i = tid; i < D; i += nthreads) U[(size_t)i * ld + i] += sigma;
-  __syncthreads();
-
-  // ---- Jacobi sweeps ---------------------------------------------------------------------
-  const int n = D + (D & 1), npairs = n >> 1, m = n - 1;
-  const float tol = a.tol;
-  int sweeps = 0;
-  for (int sweep = 0; sweep < a.max_sweeps; ++sweep) {
-    float wmax = 0.f;
-    for (int r = 0; r < m; ++r) {
-      for (int pi = warp; pi < npairs; pi += nwarps) {
-        int p, q;
-        rr_pair(n, r, pi, p, q);
-        if (p >= D || q >= D) continue;  // padding player of an odd D
-        float* up = U + (size_t)p * ld;
-        float* uq = U + (size_t)q * ld;
-        float4 av[CH], bv[CH];
-        float al = 0.f, be = 0.f, ga = 0.f;
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          const int ch = lane + 32 * c;
-          if (ch < nch) {
-            av[c] = *reinterpret_cast<const float4*>(up + 4 * ch);
-            bv[c] = *reinterpret_cast<const float4*>(uq + 4 * ch);
-          } else {
-            av[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-            bv[c] = av[c];
-          }
-          al = fmaf(av[c].x, av[c].x, fmaf(av[c].y, av[c].y, fmaf(av[c].z, av[c].z, fmaf(av[c].w, av[c].w, al))));
-          be = fmaf(bv[c].x, bv[c].x, fmaf(bv[c].y, bv[c].y, fmaf(bv[c].z, bv[c].z, fmaf(bv[c].w, bv[c].w, be))));
-          ga = fmaf(av[c].x, bv[c].x, fmaf(av[c].y, bv[c].y, fmaf(av[c].z, bv[c].z, fmaf(av[c].w, bv[c].w, ga))));
+      float bound;
+      if (attempt == 0) {
+        // power iteration on the symmetric U: ||A||_2 estimate (a lower bound, hence x1.35)
+        for (int i = tid; i < ld; i += nthreads) {
+          const unsigned h = (unsigned)(i + 1) * 2654435761u;
+          wv[i] = (i < D) ? (((h >> 8) & 0xffff) * (1.f / 32768.f) - 1.f) : 0.f;
         }
-        al = warp_sum(al);
-        be = warp_sum(be);
-        ga = warp_sum(ga);
-        const float den = al * be;
-        const float off = (den > 0.f) ? fabsf(ga) / sqrtf(den) : 0.f;
-        wmax = fmaxf(wmax, off);
-        if (off > tol) {
-          const float zeta = (be - al) / (2.f * ga);
-          const float az = fabsf(zeta);
-          float t = 1.f / (az + sqrtf(fmaf(az, az, 1.f)));
-          t = (zeta < 0.f) ? -t : t;
-          const float cs = 1.f / sqrtf(fmaf(t, t, 1.f));
-          const float sn = cs * t;
+        __syncthreads();
+        float est = 0.f;
+        for (int it = 0; it < 10; ++it) {
+          float y = 0.f;
+          if (tid < D) {
+#pragma unroll 4
+            for (int j = 0; j < D; ++j) y = fmaf(Gk[(size_t)j * ld + tid], wv[j], y);
+          }
+          const float xn = block_sum((tid < D) ? wv[tid] * wv[tid] : 0.f, red);
+          const float yn = block_sum(y * y, red);
+          est = sqrtf(yn / fmaxf(xn, 1e-30f));
+          __syncthreads();
+          if (tid < D) wv[tid] = y * rsqrtf(fmaxf(yn, 1e-30f));
+          __syncthreads();
+        }
+        bound = 1.35f * est;
+      } else {
+        const float fro = sqrtf(block_sum(fro_part, red));
+        float gmax = 0.f;
+        for (int col = warp; col < D; col += nwarps) {
+          float s = 0.f;
+          for (int r = lane; r < D; r += 32) s += fabsf(Gk[(size_t)col * ld + r]);
+          s = warp_sum(s);
+          gmax = fmaxf(gmax, s);
+        }
+        gmax = block_max(gmax, red);
+        bound = 1.25f * fminf(gmax, fro);
+      }
+      if (tid == 0) s_sigma = (bound > 0.f) ? bound : 1.0f;
+    } else if (tid == 0) {
+      s_sigma = 0.f;
+    }
+    __syncthreads();
+    sigma = s_sigma;
+    if (sigma != 0.f)
+      for (int i = tid; i < D; i += nthreads) Gk[(size_t)i * ld + i] += sigma;
+    __syncthreads();
+    if (a.keepG) {
+      if (a.warmVt != nullptr && attempt == 0) {
+        // U_0 = G V_prev, column by column in place: U[:,k] = V_prev[k][:] then U[:,k] <- G U[:,k]
+        const float* Vp = a.warmVt + base;
+        for (int idx = tid; idx < D * ld; idx += nthreads) {
+          const int col = idx / ld, row = idx - col * ld;
+          U[idx] = (row < D) ? Vp[(size_t)col * D + row] : 0.f;
+        }
+        __syncthreads();
+        for (int cb = 0; cb < D; cb += ngroups) {
+          const int col = cb + grp;
+          float4 tv[CH];
+          float* u = U + (size_t)(col < D ? col : 0) * ld;
+          group_matvec<LP, CH>(Gk, u, D, ld, nch, gl, tv);
+          __syncwarp();
+          if (col < D) {
 #pragma unroll
-          for (int c = 0; c < CH; ++c) {
-            const int ch = lane + 32 * c;
-            if (ch < nch) {
-              float4 na, nb;
-              na.x = cs * av[c].x - sn * bv[c].x;  nb.x = sn * av[c].x + cs * bv[c].x;
-              na.y = cs * av[c].y - sn * bv[c].y;  nb.y = sn * av[c].y + cs * bv[c].y;
-              na.z = cs * av[c].z - sn * bv[c].z;  nb.z = sn * av[c].z + cs * bv[c].z;
-              na.w = cs * av[c].w - sn * bv[c].w;  nb.w = sn * av[c].w + cs * bv[c].w;
-              *reinterpret_cast<float4*>(up + 4 * ch) = na;
-              *reinterpret_cast<float4*>(uq + 4 * ch) = nb;
+            for (int c = 0; c < CH; ++c) {
+              const int ch = gl + LP * c;
+              if (ch < nch) *reinterpret_cast<float4*>(u + 4 * ch) = tv[c];
             }
           }
         }
+      } else {
+        for (int idx = tid; idx < D * ld; idx += nthreads) U[idx] = Gk[idx];
       }
       __syncthreads();
     }
-    ++sweeps;
-    if (lane == 0) atomicMax(&s_flag, __float_as_uint(wmax));
+
+    // ---- Jacobi sweeps -------------------------------------------------------------------
+    for (int sweep = 0; sweep < a.max_sweeps; ++sweep) {
+      // refresh the cached squared norms
+      for (int cb = 0; cb < D; cb += ngroups) {
+        const int col = cb + grp;
+        float s = 0.f;
+        if (col < D) {
+          const float* u = U + (size_t)col * ld;
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            const int ch = gl + LP * c;
+            if (ch < nch) {
+              const float4 v = *reinterpret_cast<const float4*>(u + 4 * ch);
+              s = dot4(v, v, s);
+            }
+          }
+        }
+        s = group_sum<LP>(s);
+        if (col < D && gl == 0) nrm2[col] = s;
+      }
+      __syncthreads();
+      float wmax = 0.f;
+      for (int r = 0; r < m; ++r) {
+        for (int pb = 0; pb < npairs; pb += ngroups) {
+          const int pi = pb + grp;
+          int p = 0, q = 0;
+          bool valid = pi < npairs;
+          if (valid) {
+            rr_pair(n, r, pi, p, q);
+            valid = (p < D) && (q < D);  // padding player of an odd D
+          }
+          float* up = U + (size_t)p * ld;
+          float* uq = U + (size_t)q * ld;
+          float4 av[CH], bv[CH];
+          float ga = 0.f;
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            const int ch = gl + LP * c;
+            if (valid && ch < nch) {
+              av[c] = *reinterpret_cast<const float4*>(up + 4 * ch);
+              bv[c] = *reinterpret_cast<const float4*>(uq + 4 * ch);
+              ga = dot4(av[c], bv[c], ga);
+            } else {
+              av[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+              bv[c] = av[c];
+            }
+          }
+          ga = group_sum<LP>(ga);
+          if (valid) {
+            const float al = nrm2[p], be = nrm2[q];
+            const float den = al * be;
+            const float off = (den > 0.f) ? fabsf(ga) * rsqrtf(den) : 0.f;
+            wmax = fmaxf(wmax, off);
+            if (off > tol) {
+              const float d = be - al, g2 = 2.f * ga;
+              const float h = sqrtf(fmaf(d, d, g2 * g2));
+              float t = __fdividef(fabsf(g2), fabsf(d) + h);
+              t = ((d < 0.f) != (g2 < 0.f)) ? -t : t;
+              const float x = fmaf(t, t, 1.f);
+              float cs = rsqrtf(x);
+              cs = cs * fmaf(-0.5f * x, cs * cs, 1.5f);  // one Newton step: ~0.5 ulp
+              const float sn = t * cs;
+              const float tau = __fdividef(sn, 1.f + cs);
+#pragma unroll
+              for (int c = 0; c < CH; ++c) {
+                const int ch = gl + LP * c;
+                if (ch < nch) {
+                  float4 na, nb;
+                  na.x = av[c].x - sn * fmaf(tau, av[c].x, bv[c].x);  nb.x = bv[c].x + sn * fmaf(-tau, bv[c].x, av[c].x);
+                  na.y = av[c].y - sn * fmaf(tau, av[c].y, bv[c].y);  nb.y = bv[c].y + sn * fmaf(-tau, bv[c].y, av[c].y);
+                  na.z = av[c].z - sn * fmaf(tau, av[c].z, bv[c].z);  nb.z = bv[c].z + sn * fmaf(-tau, bv[c].z, av[c].z);
+                  na.w = av[c].w - sn * fmaf(tau, av[c].w, bv[c].w);  nb.w = bv[c].w + sn * fmaf(-tau, bv[c].w, av[c].w);
+                  *reinterpret_cast<float4*>(up + 4 * ch) = na;
+                  *reinterpret_cast<float4*>(uq + 4 * ch) = nb;
+                }
+              }
+              if (gl == 0) {
+                nrm2[p] = fmaxf(fmaf(-t, ga, al), 0.f);
+                nrm2[q] = fmaf(t, ga, be);
+              }
+            }
+          }
+        }
+        __syncthreads();
+      }
+      ++sweeps;
+      wmax = warp_max(wmax);
+      if (lane == 0) atomicMax(&s_flag, __float_as_uint(wmax));
+      __syncthreads();
+      const float fmaxoff = __uint_as_float(s_flag);
+      __syncthreads();
+      if (tid == 0) s_flag = 0u;
+      if (fmaxoff <= tol) break;
+    }
+
+    // ---- column norms ----------------------------------------------------------------------
+    float wsum_part = 0.f;
+    for (int col = warp; col < D; col += nwarps) {
+      const float* u = U + (size_t)col * ld;
+      float s = 0.f;
+      for (int r = lane; r < D; r += 32) s = fmaf(u[r], u[r], s);
+      s = warp_sum(s);
+      const float nrm = sqrtf(s);
+      if (lane == 0) {
+        wv[col] = nrm;
+        wsum_part += nrm;
+      }
+    }
+    wsum = block_sum(wsum_part, red);
     __syncthreads();
-    const float fmaxoff = __uint_as_float(s_flag);
-    __syncthreads();
-    if (tid == 0) s_flag = 0u;
-    if (fmaxoff <= tol) break;
+    if (a.shift_mode != 1 || attempt == 1) break;
+    const float expect = trace + (float)D * sigma;
+    if (fabsf(wsum - expect) <= 2e-3f * fabsf(expect)) break;  // A + sigma I was positive definite
+    sweeps += 1000;                                            // mark the retry in info[0]
   }
 
-  // ---- eigenvalues = column norms - sigma, eigenvectors = normalised columns -------------
+  // ---- eigenvalues = column norms - sigma, eigenvectors = normalised columns ---------------
   float* Vb = a.Vt + (size_t)b * D * D;
   for (int col = warp; col < D; col += nwarps) {
     const float* u = U + (size_t)col * ld;
-    float s = 0.f;
-    for (int r = lane; r < D; r += 32) s = fmaf(u[r], u[r], s);
-    s = warp_sum(s);
-    const float nrm = sqrtf(s);
+    const float nrm = wv[col];
     const float inv = (nrm > 0.f) ? 1.f / nrm : 0.f;
     for (int r = lane; r < D; r += 32) Vb[(size_t)col * D + r] = u[r] * inv;
-    if (lane == 0) wv[col] = nrm - sigma;
   }
   __syncthreads();
-  float wsum_part = 0.f;
-  for (int i = tid; i < D; i += nthreads) {
-    a.w[(size_t)b * D + i] = wv[i];
-    wsum_part += wv[i];
+  if (a.keepG) {
+    // Rayleigh quotients with the kept G = A + sigma I: lambda_k = u^T G u / u^T u - sigma
+    for (int cb = 0; cb < D; cb += ngroups) {
+      const int col = cb + grp;
+      const float* u = U + (size_t)(col < D ? col : 0) * ld;
+      float4 tv[CH];
+      group_matvec<LP, CH>(Gk, u, D, ld, nch, gl, tv);
+      float num = 0.f, den = 0.f;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int ch = gl + LP * c;
+        if (ch < nch) {
+          const float4 uv = *reinterpret_cast<const float4*>(u + 4 * ch);
+          num = dot4(tv[c], uv, num);
+          den = dot4(uv, uv, den);
+        }
+      }
+      num = group_sum<LP>(num);
+      den = group_sum<LP>(den);
+      if (col < D && gl == 0) nrm2[col] = (den > 0.f) ? num / den : 0.f;
+    }
+    __syncthreads();
+    for (int i = tid; i < D; i += nthreads) wv[i] = nrm2[i];
+    __syncthreads();
   }
-  const float wsum = block_sum(wsum_part, red);
+  for (int i = tid; i < D; i += nthreads) {
+    const float ev = wv[i] - sigma;
+    wv[i] = ev;
+    a.w[(size_t)b * D + i] = ev;
+  }
+  wsum -= (float)D * sigma;
   if (a.info && tid == 0) {
     float* o = a.info + (size_t)b * 4;
     o[0] = (float)sweeps;
@@ -193,6 +381,7 @@ __global__ void __launch_bounds__(1024, 1) eig_jacobi_small_kernel(EigArgs a) {
     o[2] = trace;
     o[3] = wsum;
   }
+  __syncthreads();
 
   // ---- tails -----------------------------------------------------------------------------
   if (a.tail == TAIL_LAYER) {
@@ -244,6 +433,30 @@ __global__ void __launch_bounds__(1024, 1) eig_jacobi_small_kernel(EigArgs a) {
   }
 }
 
+static int g_tune_lp = 0;      // 0 = auto; otherwise force lanes per column pair (4/8/16/32)
+static int g_tune_keepg = -1;  // -1 = auto (keep G when two buffers fit); 0 / 1 force
+int eig_small_tune(const char* key, int value) {
+  if (!strcmp(key, "eig_lp")) { g_tune_lp = value; return 0; }
+  if (!strcmp(key, "eig_keepg")) { g_tune_keepg = value; return 0; }
+  return 1;
+}
+
+template <int LP, int CH>
+static int launch_cfg(const EigArgs& a, int B, size_t smem, cudaStream_t st) {
+  const int npairs = (a.D + 1) / 2;
+  int threads = ((npairs * LP + 31) / 32) * 32;
+  if (threads > eig_max_threads(LP, CH)) threads = eig_max_threads(LP, CH);
+  if (threads < 128) threads = 128;
+  if (threads < a.D) threads = ((a.D + 31) / 32) * 32;  // the power iteration wants a thread per row
+  UGLAD_CUDA(cudaFuncSetAttribute(eig_jacobi_small_kernel<LP, CH>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  profile_begin(st);
+  eig_jacobi_small_kernel<LP, CH><<<B, threads, smem, st>>>(a);
+  profile_end(st);
+  UGLAD_CHECK_LAUNCH("eig_jacobi_small_kernel");
+  return 0;
+}
+
 int launch_eig_small(const EigArgs& a_in, int B, cudaStream_t st) {
   EigArgs a = a_in;
   a.ld = (a.D + 3) & ~3;
@@ -251,20 +464,27 @@ int launch_eig_small(const EigArgs& a_in, int B, cudaStream_t st) {
     set_error("eig_small: D=%d exceeds the shared-memory solver limit %d", a.D, UGLAD_SMALL_D_MAX);
     return 1;
   }
-  const size_t smem = ((size_t)a.ld * a.D + a.ld + 2) * sizeof(float) + 32 * sizeof(double) + 32 * sizeof(float) + 16;
-  const int npairs = (a.D + 1) / 2;
-  int nwarps = npairs < 4 ? 4 : (npairs > 32 ? 32 : npairs);
-  if (B >= 148 && nwarps > 16) nwarps = 16;  // throughput mode: more CTAs per SM
-  const int threads = nwarps * 32;
-  if (a.ld <= 128) {
-    UGLAD_CUDA(cudaFuncSetAttribute(eig_jacobi_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    eig_jacobi_small_kernel<1><<<B, threads, smem, st>>>(a);
-  } else {
-    UGLAD_CUDA(cudaFuncSetAttribute(eig_jacobi_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    eig_jacobi_small_kernel<2><<<B, threads, smem, st>>>(a);
-  }
-  UGLAD_CHECK_LAUNCH("eig_jacobi_small_kernel");
-  return 0;
+  const size_t mat = (size_t)a.ld * a.D * sizeof(float);
+  const size_t extra = 2 * a.ld * sizeof(float) + 32 * sizeof(double) + 32 * sizeof(float) + 16;
+  const bool fits2 = 2 * mat + extra <= 227 * 1024;
+  a.keepG = (g_tune_keepg < 0) ? (fits2 ? 1 : 0) : (g_tune_keepg && fits2 ? 1 : 0);
+  if (!a.keepG) a.warmVt = nullptr;
+  const size_t smem = (a.keepG ? 2 : 1) * mat + extra;
+  const int nch = a.ld / 4;
+  // lanes per column pair: narrow groups replicate the rotation scalar math less (the kernel
+  // is issue-bound), wide groups shorten the per-round dependent chain.
+  int lp = g_tune_lp;
+  if (lp == 0) lp = (nch <= 8) ? 4 : (nch <= 32 ? 8 : 16);
+  while (lp < 32 && lp * 8 < nch) lp *= 2;
+  const int ch = (nch + lp - 1) / lp;
+#define UGLAD_EIG_CASE(LP_, CH_) if (lp == LP_ && ch <= CH_) return launch_cfg<LP_, CH_>(a, B, smem, st)
+  UGLAD_EIG_CASE(4, 2); UGLAD_EIG_CASE(4, 4); UGLAD_EIG_CASE(4, 8);
+  UGLAD_EIG_CASE(8, 1); UGLAD_EIG_CASE(8, 2); UGLAD_EIG_CASE(8, 4); UGLAD_EIG_CASE(8, 8);
+  UGLAD_EIG_CASE(16, 1); UGLAD_EIG_CASE(16, 2); UGLAD_EIG_CASE(16, 4);
+  UGLAD_EIG_CASE(32, 1); UGLAD_EIG_CASE(32, 2);
+#undef UGLAD_EIG_CASE
+  set_error("eig_small: no kernel configuration for D=%d lp=%d", a.D, lp);
+  return 1;
 }
 
 }  // namespace uglad

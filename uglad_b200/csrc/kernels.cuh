@@ -22,12 +22,18 @@ struct EigArgs {
   float* sroot = nullptr;        // TAIL_LAYER: eigenvalues s of the (Newton-Schulz) root
   float* snorm = nullptr;        // TAIL_LAYER: [B] ||s||_2 ; TAIL_LOSS: [B] logdet
   float* scratch = nullptr;      // large-D path only
+  const float* warmVt = nullptr; // optional [B][D][D] eigenvectors of a nearby matrix (warm start)
+  int keepG = 0;                 // set by the launcher: second shared-memory buffer holds A + sigma I
   int D = 0, ld = 0, build = 0, shift_mode = 1, tail = TAIL_PLAIN, exact_sqrt = 0;
   int max_sweeps = 40;
   float tol = 1e-6f;
 };
 int launch_eig_small(const EigArgs& a, int B, cudaStream_t st);
+int eig_small_tune(const char* key, int value);
 int launch_eig(const EigArgs& a, int B, cudaStream_t st);  // dispatch on D
+// optional CUDA-event bracket around the eigensolver launches (bench.py's roofline leg)
+void profile_begin(cudaStream_t st);
+void profile_end(cudaStream_t st);
 size_t eig_scratch_floats(int B, int D);
 
 // ---- batched SGEMM ------------------------------------------------------------------------

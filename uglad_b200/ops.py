@@ -99,6 +99,19 @@ def make_dims(B, D, L, H, init_diag, B_total=None, exact_sqrt=False, lambda_init
                      int(bool(exact_sqrt)), float(lambda_init))
 
 
+_warm: dict = {}
+warm_start_enabled = True
+
+
+def reset_warm_start():
+    """Forget the eigenvector seed (the next forward solves from scratch)."""
+    _warm.clear()
+
+
+def tune(key: str, value: int):
+    check(_lib.load().uglad_tune(key.encode(), int(value)), "uglad_tune")
+
+
 class GladFunction(torch.autograd.Function):
     """theta_pred = glad(S; params)  (glad.py:74-150) with the hand-written backward."""
 
@@ -124,12 +137,16 @@ class GladFunction(torch.autograd.Function):
         if n == 0:
             raise _lib.UgladError(lib.uglad_last_error().decode())
         ws = torch.empty(n, device=S.device, dtype=torch.float32)
+        # warm start: the previous forward's workspace for the same problem shape (normally the
+        # previous epoch of the same fit) seeds the eigensolver; see uglad_glad_forward.
+        wkey = (B, D, L, H, init_diag, S.device.index)
+        warm = _warm.get(wkey) if warm_start_enabled else None
         eig = _eig_of(S) if init_diag == 0 else None
         wS, VtS = (eig.wS, eig.VtS) if eig is not None else (None, None)
         st = _stream(S)
         if world == 1:
             check(lib.uglad_glad_forward(C.byref(dims), _ptr(S), _ptr(flat_params), _ptr(wS), _ptr(VtS),
-                                         _ptr(ws), st), "uglad_glad_forward")
+                                         _ptr(ws), _ptr(warm), st), "uglad_glad_forward")
         else:
             import torch.distributed as dist
             check(lib.uglad_glad_init_forward(C.byref(dims), _ptr(S), _ptr(flat_params), _ptr(wS), _ptr(VtS),
@@ -137,10 +154,13 @@ class GladFunction(torch.autograd.Function):
             off = lib.uglad_workspace_offset(C.byref(dims), b"normf")
             normf = ws[off:off + L]
             for k in range(L):
-                check(lib.uglad_glad_layer_forward(C.byref(dims), k, _ptr(S), _ptr(flat_params), _ptr(ws), st),
-                      "uglad_glad_layer_forward")
+                check(lib.uglad_glad_layer_forward(C.byref(dims), k, _ptr(S), _ptr(flat_params), _ptr(ws),
+                                                   _ptr(warm), st), "uglad_glad_layer_forward")
                 if k + 1 < L:  # the mean of glad.py:147 runs over every process's graphs
                     dist.all_reduce(normf[k:k + 1], group=group)
+        if warm_start_enabled:
+            _warm.clear()  # keep exactly one earlier workspace alive
+            _warm[wkey] = ws
         off = lib.uglad_workspace_offset(C.byref(dims), b"theta")
         theta = ws[off:off + B * D * D].view(B, D, D)
         ctx.dims, ctx.ws, ctx.S, ctx.params, ctx.eig, ctx.group, ctx.world = dims, ws, S, flat_params, eig, group, world
