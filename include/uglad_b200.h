@@ -61,6 +61,16 @@ int uglad_eigh(const float* A, int B, int D, int shift_mode, float* w, float* Vt
  * diagonal of S (in place) and to wS.  wS / VtS are reused by every later forward.        */
 int uglad_condition_covariance(float* S, int B, int D, float offset, float* wS, float* VtS,
                                float* info, float* scratch, void* stream);
+/* D > uglad_small_d_max(): the large-D path keeps no eigendecomposition (wS / VtS / info are
+ * ignored and may be NULL); the repair decision is a Cholesky test of S - 1e-6 I and, for the
+ * graphs that fail it, a bisection on the shift.  Host-synchronous.  scratch must hold
+ * uglad_condition_scratch_floats(B, D) floats (for D <= small max that equals
+ * uglad_eigh_scratch_floats).                                                             */
+size_t uglad_condition_scratch_floats(int B, int D);
+/* largest D served by the one-CTA eigensolver; above it the theta update runs the reference's
+ * Newton-Schulz iteration as dense products (tcgen05 3xTF32) and logdet / inverses come from a
+ * blocked Cholesky.  uglad_eigh itself is only available up to this size.                  */
+int uglad_small_d_max(void);
 
 /* (2)+(3) the unrolled model.  The workspace holds everything the backward needs
  * (theta_k1, theta_pred, eigenvectors, eigenvalues per layer) plus scratch.              */

@@ -261,3 +261,89 @@ def test_size_independent_properties_at_full_size(dev):
         th_p = ug.glad.glad(S[perm].contiguous(), model, L=15).clone()
     assert rel(th.cpu().numpy(), th.transpose(1, 2).cpu().numpy()) < 1e-5
     assert rel(th_p.cpu().numpy(), th[perm].cpu().numpy()) < 1e-5
+
+
+# ---- large-D path (Newton-Schulz as dense products + blocked Cholesky) ---------------------------
+@pytest.fixture
+def force_large_path():
+    """Lower the eigensolver/large-D threshold to 0 so that the large-D kernels run on the small
+    golden problems too (the threshold only selects the algorithm, never the result)."""
+    from uglad_b200 import ops
+    ops.tune("small_d_max", 0)
+    ops.reset_warm_start()
+    yield
+    ops.tune("small_d_max", 232)
+    ops.reset_warm_start()
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
+def test_large_path_forward_backward_against_reference_golden(dev, force_large_path, path):
+    from uglad_b200 import main as ug
+    g = np.load(path)
+    L, idg = int(g["L"]), int(g["init_diag"])
+    S = torch.tensor(g["S"], device=dev)
+    model = load_model(g, "p0")
+    theta, loss = ug.forward_uGLAD(S, model, L=L, INIT_DIAG=idg)
+    loss.backward()
+    th = theta.detach().cpu().numpy()
+    assert rel(th, g["theta0"]) < THETA_TOL
+    assert edge_sets_match(th, g["theta0"])
+    assert abs(loss.item() - float(g["loss0"])) < 1e-4 * max(1.0, abs(float(g["loss0"])))
+    for k, p in model.named_parameters():
+        assert rel(p.grad.cpu().numpy(), g["g0/" + k]) < 1e-3, k
+
+
+@pytest.mark.parametrize("D,B,L", [(233, 2, 4), (320, 1, 3)])
+def test_large_path_matches_oracle_above_the_threshold(dev, D, B, L):
+    """Sizes the one-CTA eigensolver cannot hold, including a D that is not a multiple of 4."""
+    from uglad_b200 import main as ug, ops
+    from uglad_b200.glad.glad_params import GladParams
+    ops.reset_warm_start()
+    rng = np.random.default_rng(D)
+    X = rng.random((B, 2 * D, D))
+    S = torch.tensor(O.covariance(X), dtype=torch.float32)
+    P = O.init_params(D)
+    model = GladParams(1.0, 3, 3)
+    model.load_state_dict({k: v.detach() for k, v in P.items()})
+    th_o, loss_o = O.forward_loss(S, P, L, 0)
+    loss_o.backward()
+    th, loss = ug.forward_uGLAD(S.to(dev), model, L=L, INIT_DIAG=0)
+    loss.backward()
+    assert rel(th.detach().cpu().numpy(), th_o.detach().numpy()) < THETA_TOL
+    assert abs(loss.item() - loss_o.item()) < 1e-4 * max(1.0, abs(loss_o.item()))
+    for k, p in model.named_parameters():
+        assert rel(p.grad.cpu().numpy(), P[k].grad.numpy()) < 1e-3, k
+
+
+@pytest.mark.parametrize("D,B", [(70, 3), (129, 2), (300, 2)])
+def test_cholesky_loss_and_gradient(dev, force_large_path, D, B):
+    from uglad_b200 import main as ug
+    rng = np.random.default_rng(D + 1)
+    A = rng.standard_normal((B, D, 2 * D))
+    theta = torch.tensor(A @ A.transpose(0, 2, 1) / D + 0.5 * np.eye(D), dtype=torch.float32)
+    S = torch.tensor(rng.standard_normal((B, D, D)), dtype=torch.float32)
+    S = S + S.transpose(1, 2)
+    t_o = theta.clone().requires_grad_(True)
+    loss_o = O.glasso_loss(t_o, S)
+    loss_o.backward()
+    t_g = theta.to(dev).requires_grad_(True)
+    loss = ug.loss_uGLAD(t_g, S.to(dev))
+    loss.backward()
+    assert abs(loss.item() - loss_o.item()) < 1e-5 * max(1.0, abs(loss_o.item()))
+    assert rel(t_g.grad.cpu().numpy(), t_o.grad.numpy()) < 2e-5
+
+
+def test_large_path_indefinite_theta_gives_nan_loss(dev, force_large_path):
+    from uglad_b200 import main as ug
+    theta = torch.tensor(np.diag([1.0, -2.0, 3.0])[None], dtype=torch.float32, device=dev)
+    assert torch.isnan(ug.loss_uGLAD(theta, torch.eye(3, device=dev)[None]))
+
+
+@pytest.mark.parametrize("M,D", [(5, 12), (40, 70), (300, 40)])
+def test_large_path_covariance_repair(dev, force_large_path, M, D):
+    """prepare_data.py:345-355 without an eigensolver: Cholesky test + bisection on the shift."""
+    from uglad_b200.utils import prepare_data
+    rng = np.random.default_rng(M)
+    X = rng.standard_normal((2, M, D))
+    S = prepare_data.get_covariance(X, offset=0.1).cpu().numpy()
+    assert rel(S, O.covariance(X, offset=0.1)) < 2e-5

@@ -42,13 +42,19 @@ void profile_end(cudaStream_t st) {
   if (!g_prof_events.empty()) cudaEventRecord(g_prof_events.back().second, st);
 }
 
+// runtime threshold between the eigensolver path and the large-D path (tests lower it to run the
+// large-D kernels on small problems); never above the shared-memory solver's hard limit
+static int g_small_d_max = UGLAD_SMALL_D_MAX;
+static inline int small_d_max() { return g_small_d_max; }
+
 static inline size_t al4(size_t x) { return (x + 3) & ~(size_t)3; }
 
 struct Ws {
   size_t theta, X, Vt, beta, sroot, f, snorm, lam, lamfeat, normf, info, part, counter, f0;
-  size_t T1, T2, G0, G1, GF3, rho_part, trh_part, sgb_part, t0_part, eig_scratch, total;
+  size_t T1, T2, G0, G1, GF3, rho_part, trh_part, sgb_part, t0_part, eig_scratch, ns_scratch, chol_scratch, total;
   size_t n1, n2, nblk;
   int NPR;
+  bool large;   // D > small_d_max(): Newton-Schulz GEMM path, no eigenvectors are stored
 };
 static Ws ws_layout(const uglad_dims* d) {
   Ws w;
@@ -57,11 +63,12 @@ static Ws ws_layout(const uglad_dims* d) {
   w.n2 = B * D * D;
   w.nblk = (size_t)elem_blocks_per_graph(d->D) * B;
   w.NPR = rho_param_count(d->H);
+  w.large = d->D > small_d_max();
   size_t o = 0;
   auto take = [&](size_t n) { size_t r = o; o += al4(n); return r; };
   w.theta = take((L + 1) * w.n2);
   w.X = take(L * w.n2);
-  w.Vt = take(L * w.n2);
+  w.Vt = take(w.large ? 0 : L * w.n2);
   w.beta = take(L * w.n1);
   w.sroot = take(L * w.n1);
   w.f = take(L * w.n1);
@@ -83,6 +90,8 @@ static Ws ws_layout(const uglad_dims* d) {
   w.sgb_part = take(L * w.nblk);
   w.t0_part = take(w.nblk);
   w.eig_scratch = take(eig_scratch_floats(d->B, d->D));
+  w.ns_scratch = take(w.large ? ns_scratch_floats(d->B, d->D) : 0);
+  w.chol_scratch = take(w.large ? chol_scratch_floats(d->B, d->D) : 0);
   w.total = o;
   return w;
 }
@@ -92,6 +101,10 @@ static int check_dims(const uglad_dims* d) {
   if (d->B <= 0 || d->D <= 0 || d->L <= 0) { set_error("bad dims B=%d D=%d L=%d", d->B, d->D, d->L); return 1; }
   if (d->H <= 0 || d->H > UGLAD_MAX_H) { set_error("H=%d outside [1,%d]", d->H, UGLAD_MAX_H); return 1; }
   if (d->B_total < d->B) { set_error("B_total=%d < B=%d", d->B_total, d->B); return 1; }
+  if (d->D > small_d_max() && d->exact_sqrt) {
+    set_error("exact_sqrt is only available on the eigensolver path (D <= %d)", small_d_max());
+    return 1;
+  }
   return 0;
 }
 
@@ -105,7 +118,7 @@ static int spectral_recon(const float* Vt, const float* f, float* C, int B, int 
   g.sA = g.sB = g.sC = (long long)D * D;
   g.transA = 1; g.transB = 0;
   g.kscale = f; g.sK = D;
-  g.alpha = alpha; g.E1 = E1; g.sE1 = sE1; g.lde1 = D;
+  g.alpha = alpha; g.beta = alpha; g.E1 = E1; g.sE1 = sE1; g.lde1 = D;
   return launch_gemm(g, B, st);
 }
 static int bgemm(const float* A, int tA, const float* Bm, int tB, float* C, int B, int D, cudaStream_t st) {
@@ -120,13 +133,12 @@ static int bgemm(const float* A, int tA, const float* Bm, int tB, float* C, int 
 
 int launch_eig(const EigArgs& a, int B, cudaStream_t st) {
   if (a.D <= UGLAD_SMALL_D_MAX) return launch_eig_small(a, B, st);
-  set_error("eigensolver: D=%d > %d needs the blocked large-D path (not built yet)", a.D, UGLAD_SMALL_D_MAX);
+  set_error("eigensolver: D=%d > %d; the large-D path does not use an eigendecomposition (DESIGN.md)", a.D, UGLAD_SMALL_D_MAX);
   return 1;
 }
 size_t eig_scratch_floats(int B, int D) {
-  (void)B;
-  if (D <= UGLAD_SMALL_D_MAX) return 0;
-  return 0;
+  (void)B; (void)D;
+  return 0;  // the shared-memory solver needs no global scratch
 }
 
 }  // namespace uglad
@@ -165,11 +177,74 @@ int uglad_eigh(const float* A, int B, int D, int shift_mode, float* w, float* Vt
   return launch_eig(a, B, (cudaStream_t)stream);
 }
 
+// prepare_data.py:345-355 for D > small_d_max(): "min eig <= 1e-6" is decided by a Cholesky
+// factorisation of S - 1e-6 I; only graphs that fail it need the eigenvalue itself, found by
+// exponential search + bisection on the shift (host-driven: this runs once per fit).
+static int condition_large(float* S, int B, int D, float offset, float* scratch, cudaStream_t st) {
+  const size_t n2 = (size_t)B * D * D;
+  float* T = scratch;
+  float* mu_dev = T + al4(n2);
+  float* cs = mu_dev + al4(B);
+  std::vector<float> lo(B), hi(B, 1e-6f), mu(B, 1e-6f), step(B, 1e-6f);
+  std::vector<int> fail(B), found_lo(B, 0), need(B, 0);
+  auto test = [&]() -> int {
+    UGLAD_CUDA(cudaMemcpyAsync(mu_dev, mu.data(), B * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (launch_copy_shift(S, (long long)D * D, B, D, 0.f, nullptr, T, st)) return 1;
+    if (chol_factor(T, B, D, 0.f, mu_dev, nullptr, cs, st)) return 1;
+    UGLAD_CUDA(cudaMemcpyAsync(fail.data(), chol_fail_flags(cs, B, D), B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    UGLAD_CUDA(cudaStreamSynchronize(st));
+    return 0;
+  };
+  if (test()) return 1;
+  bool any = false;
+  for (int b = 0; b < B; ++b) { need[b] = fail[b]; any |= fail[b] != 0; }
+  if (!any) return 0;
+  // invariant: S - hi I is not positive definite (hi >= min eig); search lo with S - lo I positive definite
+  for (int it = 0; it < 64; ++it) {
+    bool pending = false;
+    for (int b = 0; b < B; ++b) {
+      if (!need[b]) { mu[b] = 0.f; continue; }   // result ignored
+      if (!found_lo[b]) { mu[b] = hi[b] - step[b]; pending = true; }
+      else if (hi[b] - lo[b] > 2e-8f * fmaxf(1.f, fabsf(lo[b]) * 1e2f)) { mu[b] = 0.5f * (lo[b] + hi[b]); pending = true; }
+      else mu[b] = lo[b];
+    }
+    if (!pending) break;
+    if (test()) return 1;
+    for (int b = 0; b < B; ++b) {
+      if (!need[b]) continue;
+      if (!found_lo[b]) {
+        if (fail[b]) { hi[b] = mu[b]; step[b] *= 4.f; }
+        else { lo[b] = mu[b]; found_lo[b] = 1; }
+      } else if (hi[b] - lo[b] > 2e-8f * fmaxf(1.f, fabsf(lo[b]) * 1e2f)) {
+        if (fail[b]) hi[b] = mu[b]; else lo[b] = mu[b];
+      }
+    }
+  }
+  std::vector<float> add(B, 0.f);
+  for (int b = 0; b < B; ++b)
+    if (need[b]) add[b] = offset - 0.5f * (lo[b] + hi[b]);
+  UGLAD_CUDA(cudaMemcpyAsync(mu_dev, add.data(), B * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (launch_add_diag(S, B, D, mu_dev, st)) return 1;
+  UGLAD_CUDA(cudaStreamSynchronize(st));  // `add` lives on this stack frame
+  return 0;
+}
+
+size_t uglad_condition_scratch_floats(int B, int D) {
+  if (D <= small_d_max()) return eig_scratch_floats(B, D);
+  return al4((size_t)B * D * D) + al4(B) + al4(chol_scratch_floats(B, D));
+}
+
 int uglad_condition_covariance(float* S, int B, int D, float offset, float* wS, float* VtS,
                                float* info, float* scratch, void* stream) {
+  if (D > small_d_max()) {
+    if (!S || !scratch || B <= 0) { set_error("condition_covariance: bad arguments"); return 1; }
+    return condition_large(S, B, D, offset, scratch, (cudaStream_t)stream);
+  }
   if (uglad_eigh(S, B, D, 1, wS, VtS, info, scratch, stream)) return 1;
   return launch_condition(S, wS, B, D, offset, (cudaStream_t)stream);
 }
+
+int uglad_small_d_max(void) { return small_d_max(); }
 
 size_t uglad_workspace_floats(const uglad_dims* d) {
   if (check_dims(d)) return 0;
@@ -199,7 +274,14 @@ int uglad_glad_init_forward(const uglad_dims* d, const float* S, const float* pa
   cudaStream_t st = (cudaStream_t)stream;
   const Ws w = ws_layout(d);
   UGLAD_CUDA(cudaMemsetAsync(ws + w.counter, 0, 4 * sizeof(float), st));
+  if (w.large && ns_scratch_init(ws + w.ns_scratch, d->B, d->D, st)) return 1;
   if (d->init_diag == 1) return launch_theta_init_diag(S, params, d->B, d->D, ws + w.theta, st);
+  if (w.large) {  // theta_0 = (S + t I)^-1 by Cholesky
+    float* cs = ws + w.chol_scratch;
+    if (launch_copy_shift(S, (long long)d->D * d->D, d->B, d->D, 0.f, params, ws + w.T1, st)) return 1;
+    if (chol_factor(ws + w.T1, d->B, d->D, 0.f, nullptr, nullptr, cs, st)) return 1;
+    return chol_inverse(ws + w.T1, d->B, d->D, ws + w.T2, ws + w.theta, 1.f, nullptr, 0, 0.f, cs, st);
+  }
   if (!wS || !VtS) { set_error("glad_init_forward: INIT_DIAG=0 needs the eigen-decomposition of S"); return 1; }
   if (launch_init_f(wS, params, d->B, d->D, ws + w.f0, st)) return 1;
   return spectral_recon(VtS, ws + w.f0, ws + w.theta, d->B, d->D, 1.f, nullptr, 0, st);
@@ -219,6 +301,12 @@ int uglad_glad_layer_forward(const uglad_dims* d, int k, const float* S, const f
   float* fk = ws + w.f + (size_t)k * w.n1;
   if (launch_lambda_step(k, params, d->H, d->lambda_init, d->B_total, ws + w.normf, ws + w.lam,
                          ws + w.lamfeat, st)) return 1;
+  if (w.large) {
+    if (ns_theta_update_forward(S, (long long)D * D, theta_prev, ws + w.lam + k, B, D, Xk, ws + w.ns_scratch, st))
+      return 1;
+    return launch_z_update_fwd(Xk, S, theta_prev, params, d->H, B, D, theta_next, ws + w.part,
+                               ws + w.normf + k, reinterpret_cast<unsigned*>(ws + w.counter), st);
+  }
   EigArgs a;
   a.build = 1; a.S = S; a.Theta = theta_prev; a.lam = ws + w.lam + k; a.strideS = (long long)D * D;
   a.w = ws + w.beta + (size_t)k * w.n1; a.Vt = Vk; a.info = ws + w.info + (size_t)k * B * 4;
@@ -263,6 +351,15 @@ int uglad_glad_backward(const uglad_dims* d, const float* S, const float* params
     const float* Vk = ws + w.Vt + (size_t)k * w.n2;
     if (launch_z_update_bwd(G, Xk, S, theta_prev, params, d->H, B, D, T1, GF3,
                             ws + w.rho_part + (size_t)k * w.nblk * w.NPR, st)) return 1;
+    if (w.large) {
+      if (ns_theta_update_backward(S, (long long)D * D, theta_prev, Xk, ws + w.lam + k, T1, B, D, T2,
+                                   ws + w.trh_part + (size_t)k * w.nblk, elem_blocks_per_graph(D),
+                                   ws + w.ns_scratch, st)) return 1;
+      float* Gn = Gbuf[k & 1];
+      if (launch_gb_finish(T2, GF3, S, B, D, Gn, ws + w.sgb_part + (size_t)k * w.nblk, st)) return 1;
+      G = Gn;
+      continue;
+    }
     if (bgemm(T1, 0, Vk, 1, T2, B, D, st)) return 1;   // T2 = GX V
     if (bgemm(Vk, 0, T2, 0, T1, B, D, st)) return 1;   // T1 = V^T GX V
     if (launch_phi(T1, ws + w.beta + (size_t)k * w.n1, ws + w.sroot + (size_t)k * w.n1,
@@ -288,6 +385,7 @@ int uglad_glad_backward(const uglad_dims* d, const float* S, const float* params
 
 size_t uglad_loss_scratch_floats(int B, int D) {
   const size_t n2 = (size_t)B * D * D, n1 = (size_t)B * D;
+  if (D > small_d_max()) return 2 * al4(n2) + 2 * al4(B) + 8 + al4(chol_scratch_floats(B, D));
   return al4(n2) + 2 * al4(n1) + 2 * al4(B) + al4(4 * (size_t)B) + 8 + al4(eig_scratch_floats(B, D));
 }
 
@@ -297,6 +395,22 @@ int uglad_glasso_loss(const float* theta, const float* S, int B, int D, int S_ba
   if (S_batch != 1 && S_batch != B) { set_error("glasso_loss: S_batch=%d must be 1 or B=%d", S_batch, B); return 1; }
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n2 = (size_t)B * D * D, n1 = (size_t)B * D;
+  const long long sSl = (S_batch == 1) ? 0 : (long long)D * D;
+  if (D > small_d_max()) {  // Cholesky: logdet = 2 sum log L_ii, theta^-1 = W^T W
+    float* Lf = scratch;
+    float* W = Lf + al4(n2);
+    float* logdet = W + al4(n2);
+    float* lossb = logdet + al4(B);
+    float* counter = lossb + al4(B);
+    float* cs = counter + 8;
+    UGLAD_CUDA(cudaMemsetAsync(counter, 0, 4 * sizeof(float), st));
+    if (launch_copy_shift(theta, (long long)D * D, B, D, 0.f, nullptr, Lf, st)) return 1;
+    if (chol_factor(Lf, B, D, 0.f, nullptr, logdet, cs, st)) return 1;
+    if (launch_loss_terms(theta, S, sSl, logdet, B, D, Bdiv, lossb, loss_out,
+                          reinterpret_cast<unsigned*>(counter), st)) return 1;
+    if (grad_theta) return chol_inverse(Lf, B, D, W, grad_theta, -1.0f / Bdiv, S, sSl, 1.0f / Bdiv, cs, st);
+    return 0;
+  }
   float* Vt = scratch;
   float* w = Vt + al4(n2);
   float* f = w + al4(n1);
@@ -341,6 +455,11 @@ int uglad_profile(int enable, double* total_ms, unsigned long long* launches) {
 
 int uglad_tune(const char* key, int value) {
   if (!key) return 1;
+  if (!strcmp(key, "small_d_max")) {
+    if (value < 0 || value > UGLAD_SMALL_D_MAX) { set_error("small_d_max must lie in [0, %d]", UGLAD_SMALL_D_MAX); return 1; }
+    g_small_d_max = value;
+    return 0;
+  }
   return eig_small_tune(key, value);
 }
 

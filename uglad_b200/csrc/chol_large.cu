@@ -1,0 +1,235 @@
+// Blocked Cholesky for the large-D path (D > UGLAD_SMALL_D_MAX), batched over graphs:
+//   * log det Theta and Theta^-1 for the glasso loss and its gradient (main.py:306-315),
+//   * theta_0 = (S + t I)^-1 (glad.py:115-117),
+//   * the positive-definiteness test behind the covariance repair (prepare_data.py:345-355).
+// Right-looking, block size CB = 64: the diagonal block is factored (and its triangular inverse
+// formed) by one CTA in shared memory, the panel solve and the trailing update are GEMMs.
+// A^-1 = W^T W with W = L^-1 built block row by block row from the diagonal inverses.
+#include "kernels.cuh"
+
+namespace uglad {
+
+constexpr int CB = 64;
+constexpr int CBP = CB + 1;  // padded leading dimension in shared memory
+
+// Factor the nb x nb diagonal block at (j0, j0) of every graph: A_jj = L L^T in place (lower),
+// Winv = L^-1 (dense CB x CB, zero above the diagonal and beyond nb), logdet partial
+// sum(log L_ii), fail flag when a pivot is not positive.
+__global__ void __launch_bounds__(256) chol_diag_kernel(float* A, int D, int j0, int nb, float shift,
+                                                        const float* shift_dev, float* Winv, float* logdet_part, int nparts, int jblk,
+                                                        int* fail) {
+  __shared__ float Ls[CB][CBP];
+  __shared__ float Ws[CB][CBP];
+  __shared__ int s_fail;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  float* Ab = A + (size_t)b * D * D;
+  if (tid == 0) s_fail = 0;
+  if (shift_dev) shift += shift_dev[b];
+  for (int idx = tid; idx < CB * CB; idx += 256) {
+    const int i = idx / CB, j = idx % CB;
+    float v = 0.f;
+    if (i < nb && j < nb && j <= i) {
+      v = Ab[(size_t)(j0 + i) * D + j0 + j];
+      if (i == j) v -= shift;
+    }
+    Ls[i][j] = v;
+    Ws[i][j] = 0.f;
+  }
+  __syncthreads();
+  double ld = 0.0;
+  for (int j = 0; j < nb; ++j) {
+    const float piv = Ls[j][j];
+    __syncthreads();
+    if (!(piv > 0.f)) {
+      if (tid == 0) s_fail = 1;
+      break;  // uniform: every thread read the same pivot
+    }
+    const float r = sqrtf(piv), ir = 1.f / r;
+    if (tid == 0) ld += log((double)r);
+    // scale column j
+    for (int i = j + tid; i < nb; i += 256) Ls[i][j] = (i == j) ? r : Ls[i][j] * ir;
+    __syncthreads();
+    // rank-1 update of the trailing lower triangle
+    const int m = nb - j - 1;
+    for (int idx = tid; idx < m * m; idx += 256) {
+      const int i = j + 1 + idx / m, k = j + 1 + idx % m;
+      if (k <= i) Ls[i][k] = fmaf(-Ls[i][j], Ls[k][j], Ls[i][k]);
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  const bool bad = s_fail != 0;
+  // W = L^-1 by forward substitution, one thread per column c: W[i][c] = (d_ic - sum_k L[i][k] W[k][c]) / L[i][i]
+  if (!bad && tid < nb) {
+    const int c = tid;
+    for (int i = c; i < nb; ++i) {
+      float acc = (i == c) ? 1.f : 0.f;
+      for (int k = c; k < i; ++k) acc = fmaf(-Ls[i][k], Ws[k][c], acc);
+      Ws[i][c] = acc / Ls[i][i];
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < CB * CB; idx += 256) {
+    const int i = idx / CB, j = idx % CB;
+    if (i < nb && j < nb && j <= i) Ab[(size_t)(j0 + i) * D + j0 + j] = Ls[i][j];
+    Winv[((size_t)b * CB + i) * CB + j] = bad ? 0.f : Ws[i][j];
+  }
+  if (tid == 0) {
+    logdet_part[(size_t)b * nparts + jblk] = (float)ld;
+    if (bad) fail[b] = 1;
+  }
+}
+
+// logdet[b] = 2 sum_j part[b][j], NaN when the factorisation broke down (torch.logdet of a
+// matrix with a negative determinant is NaN; main.py:307)
+__global__ void chol_logdet_kernel(const float* part, int nparts, const int* fail, float* logdet, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double s = 0.0;
+  for (int j = 0; j < nparts; ++j) s += (double)part[(size_t)b * nparts + j];
+  logdet[b] = fail[b] ? __int_as_float(0x7fc00000) : (float)(2.0 * s);
+}
+
+// copy the CB x CB diagonal inverses onto the block diagonal of W and zero the rest
+__global__ void chol_winit_kernel(const float* Winv, int D, int nblkc, float* W) {
+  const int b = blockIdx.y;
+  const size_t n = (size_t)D * D;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / D), j = (int)(idx % D);
+    float v = 0.f;
+    if (i / CB == j / CB) v = Winv[(((size_t)(i / CB) * gridDim.y + b) * CB + (i % CB)) * CB + (j % CB)];
+    W[(size_t)b * n + idx] = v;
+  }
+  (void)nblkc;
+}
+
+__global__ void chol_copy_shift_kernel(const float* __restrict__ src, long long sSrc, int D, float shift,
+                                       const float* shift_dev, float* __restrict__ dst) {
+  const size_t n = (size_t)D * D;
+  if (shift_dev) shift += shift_dev[0];
+  const float* s = src + (size_t)blockIdx.y * sSrc;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+    float v = s[idx];
+    if (idx / D == idx % D) v += shift;
+    dst[(size_t)blockIdx.y * n + idx] = v;
+  }
+}
+
+static inline size_t al4c(size_t x) { return (x + 3) & ~(size_t)3; }
+static inline int nblocks_c(int D) { return (D + CB - 1) / CB; }
+
+// scratch: Winv [nblk][B][CB][CB] | logdet parts [B][nblk] | fail [B] | Tpanel [B][CB][D]
+size_t chol_scratch_floats(int B, int D) {
+  const size_t nb = nblocks_c(D);
+  return al4c(nb * B * CB * CB) + al4c((size_t)B * nb) + al4c(B) + al4c((size_t)B * CB * D);
+}
+
+struct CholBuf { float* Winv; float* ldpart; int* fail; float* Tp; };
+static CholBuf chol_carve(float* scratch, int B, int D) {
+  const size_t nb = nblocks_c(D);
+  CholBuf c;
+  c.Winv = scratch;
+  c.ldpart = c.Winv + al4c(nb * B * CB * CB);
+  c.fail = reinterpret_cast<int*>(c.ldpart + al4c((size_t)B * nb));
+  c.Tp = reinterpret_cast<float*>(c.fail) + al4c(B);
+  return c;
+}
+
+// In-place lower Cholesky factor of (A - shift I) for every graph; logdet (may be null).
+// fail[b] (device, inside scratch) is 1 where the matrix was not positive definite.
+int chol_factor(float* A, int B, int D, float shift, const float* shift_dev, float* logdet, float* scratch,
+                cudaStream_t st) {
+  const CholBuf c = chol_carve(scratch, B, D);
+  const int nb = nblocks_c(D);
+  const long long n2 = (long long)D * D;
+  UGLAD_CUDA(cudaMemsetAsync(c.fail, 0, (size_t)B * sizeof(int), st));
+  for (int j = 0; j < nb; ++j) {
+    const int j0 = j * CB, w = (D - j0 < CB) ? D - j0 : CB;
+    float* Wj = c.Winv + (size_t)j * B * CB * CB;
+    chol_diag_kernel<<<B, 256, 0, st>>>(A, D, j0, w, shift, shift_dev, Wj, c.ldpart, nb, j, c.fail);
+    UGLAD_CHECK_LAUNCH("chol_diag_kernel");
+    const int rest = D - j0 - w;
+    if (rest <= 0) break;
+    // panel: L[i, j] = A[i, j] L_jj^-T   (in place: one CTA column covers all of K = N = w)
+    GemmArgs p;
+    p.A = A + (size_t)(j0 + w) * D + j0; p.lda = D; p.sA = n2;
+    p.Bm = Wj; p.ldb = CB; p.sB = (long long)CB * CB; p.transB = 1;
+    p.C = A + (size_t)(j0 + w) * D + j0; p.ldc = D; p.sC = n2;
+    p.M = rest; p.N = w; p.K = w;
+    if (launch_gemm(p, B, st)) return 1;
+    // trailing update (lower tiles only): A[i, i'] -= L[i, j] L[i', j]^T
+    GemmArgs u;
+    u.A = p.C; u.lda = D; u.sA = n2;
+    u.Bm = p.C; u.ldb = D; u.sB = n2; u.transB = 1;
+    u.C = A + (size_t)(j0 + w) * D + (j0 + w); u.ldc = D; u.sC = n2;
+    u.E1 = u.C; u.lde1 = D; u.sE1 = n2; u.beta = 1.f; u.alpha = -1.f;
+    u.M = rest; u.N = rest; u.K = w; u.lower_only = 1;
+    if (launch_gemm(u, B, st)) return 1;
+  }
+  if (logdet) {
+    chol_logdet_kernel<<<(B + 127) / 128, 128, 0, st>>>(c.ldpart, nb, c.fail, logdet, B);
+    UGLAD_CHECK_LAUNCH("chol_logdet_kernel");
+  }
+  return 0;
+}
+const int* chol_fail_flags(float* scratch, int B, int D) { return chol_carve(scratch, B, D).fail; }
+
+// Ainv = (L L^T)^-1 from the factor left in Lf by chol_factor (same scratch).  W: [B][D][D] work.
+int chol_inverse(const float* Lf, int B, int D, float* W, float* Ainv, float alpha, const float* E1,
+                 long long sE1, float beta, float* scratch, cudaStream_t st) {
+  const CholBuf c = chol_carve(scratch, B, D);
+  const int nb = nblocks_c(D);
+  const long long n2 = (long long)D * D;
+  dim3 grid(64, B);
+  chol_winit_kernel<<<grid, 256, 0, st>>>(c.Winv, D, nb, W);
+  UGLAD_CHECK_LAUNCH("chol_winit_kernel");
+  for (int i = 1; i < nb; ++i) {
+    const int i0 = i * CB, w = (D - i0 < CB) ? D - i0 : CB;
+    // T = L[i, 0:i0] W[0:i0, 0:i0]
+    GemmArgs t;
+    t.A = Lf + (size_t)i0 * D; t.lda = D; t.sA = n2;
+    t.Bm = W; t.ldb = D; t.sB = n2;
+    t.C = c.Tp; t.ldc = D; t.sC = (long long)CB * D;
+    t.M = w; t.N = i0; t.K = i0;
+    if (launch_gemm(t, B, st)) return 1;
+    // W[i, 0:i0] = -Winv_i T
+    GemmArgs v;
+    v.A = c.Winv + (size_t)i * B * CB * CB; v.lda = CB; v.sA = (long long)CB * CB;
+    v.Bm = c.Tp; v.ldb = D; v.sB = (long long)CB * D;
+    v.C = W + (size_t)i0 * D; v.ldc = D; v.sC = n2;
+    v.M = w; v.N = i0; v.K = w; v.alpha = -1.f;
+    if (launch_gemm(v, B, st)) return 1;
+  }
+  // Ainv = alpha W^T W + beta E1
+  GemmArgs g;
+  g.A = W; g.Bm = W; g.C = Ainv;
+  g.M = g.N = g.K = D;
+  g.lda = g.ldb = g.ldc = g.lde1 = D;
+  g.sA = g.sB = g.sC = n2;
+  g.transA = 1;
+  g.alpha = alpha; g.beta = beta; g.E1 = E1; g.sE1 = sE1;
+  return launch_gemm_auto(g, B, st);
+}
+
+int launch_copy_shift(const float* src, long long sSrc, int B, int D, float shift, const float* shift_dev,
+                      float* dst, cudaStream_t st) {
+  dim3 grid(64, B);
+  chol_copy_shift_kernel<<<grid, 256, 0, st>>>(src, sSrc, D, shift, shift_dev, dst);
+  UGLAD_CHECK_LAUNCH("chol_copy_shift_kernel");
+  return 0;
+}
+
+// S_ii += add[b]  (prepare_data.py:349-350)
+__global__ void add_diag_kernel(float* S, int D, const float* add) {
+  const float a = add[blockIdx.y];
+  float* Sb = S + (size_t)blockIdx.y * D * D;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D; i += gridDim.x * blockDim.x) Sb[(size_t)i * D + i] += a;
+}
+int launch_add_diag(float* S, int B, int D, const float* add_dev, cudaStream_t st) {
+  dim3 grid((D + 255) / 256, B);
+  add_diag_kernel<<<grid, 256, 0, st>>>(S, D, add_dev);
+  UGLAD_CHECK_LAUNCH("add_diag_kernel");
+  return 0;
+}
+
+}  // namespace uglad

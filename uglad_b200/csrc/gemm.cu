@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g) {
   const float* __restrict__ mA = g.meanA ? g.meanA + (size_t)bz * g.sMean : nullptr;
   const float* __restrict__ mB = g.meanB ? g.meanB + (size_t)bz * g.sMean : nullptr;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  if (g.lower_only && n0 >= m0 + BM) return;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int M = g.M, N = g.N, K = g.K;
 
@@ -89,8 +90,9 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g) {
     __syncthreads();
   }
 
-  float* __restrict__ C = g.C + (size_t)bz * g.sC;
-  const float* __restrict__ E1 = g.E1 ? g.E1 + (size_t)bz * g.sE1 : nullptr;
+  float* C = g.C + (size_t)bz * g.sC;
+  const float* E1 = g.E1 ? g.E1 + (size_t)bz * g.sE1 : nullptr;
+  const float alpha = g.alpha_dev ? g.alpha * g.alpha_dev[(size_t)bz * g.sAlpha] : g.alpha;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int gm = m0 + ty * 4 + i;
@@ -99,9 +101,10 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g) {
     for (int j = 0; j < 4; ++j) {
       const int gn = n0 + tx * 4 + j;
       if (gn >= N) continue;
-      float v = acc[i][j];
-      if (E1) v += E1[(size_t)gm * g.lde1 + gn];
-      C[(size_t)gm * g.ldc + gn] = g.alpha * v;
+      float v = alpha * acc[i][j];
+      if (E1) v = fmaf(g.beta, E1[(size_t)gm * g.lde1 + gn], v);
+      if (gm == gn) v += g.diag;
+      C[(size_t)gm * g.ldc + gn] = v;
     }
   }
 }
@@ -117,5 +120,8 @@ int launch_gemm(const GemmArgs& g, int batch, cudaStream_t st) {
   UGLAD_CHECK_LAUNCH("gemm_kernel");
   return 0;
 }
+
+// dispatch point for the dense D^3 products of the large-D path
+int launch_gemm_auto(const GemmArgs& g, int batch, cudaStream_t st) { return launch_gemm(g, batch, st); }
 
 }  // namespace uglad

@@ -51,12 +51,37 @@ struct GemmArgs {
   const float* meanA = nullptr;       // optional centring (covariance): A elem -= meanA[m]
   const float* meanB = nullptr;       //                                 B elem -= meanB[n]
   long long sMean = 0;
-  float alpha = 1.f;                  // C = alpha * (acc + E1)
-  const float* E1 = nullptr;
+  // epilogue: C = alpha * alpha_dev[batch] * acc + beta * E1 + diag * I
+  float alpha = 1.f;
+  const float* alpha_dev = nullptr;   // optional per-batch device scalar (stride sAlpha)
+  long long sAlpha = 0;
+  float beta = 1.f;
+  const float* E1 = nullptr;          // may alias C (each element is read, then written, by one thread)
   long long sE1 = 0;
   int lde1 = 0;
+  float diag = 0.f;
+  int lower_only = 0;                 // skip tiles strictly above the diagonal (symmetric updates)
 };
-int launch_gemm(const GemmArgs& g, int batch, cudaStream_t st);
+int launch_gemm(const GemmArgs& g, int batch, cudaStream_t st);       // FP32 SIMT kernel
+int launch_gemm_auto(const GemmArgs& g, int batch, cudaStream_t st);  // tcgen05 3xTF32 when the shape allows
+
+// ---- large-D path: Newton-Schulz in GEMM form (ns_large.cu), blocked Cholesky (chol_large.cu)
+size_t ns_scratch_floats(int B, int D);
+int ns_scratch_init(float* scratch, int B, int D, cudaStream_t st);
+int ns_theta_update_forward(const float* S, long long sS, const float* Theta, const float* lam, int B, int D,
+                            float* X, float* scratch, cudaStream_t st);
+int ns_theta_update_backward(const float* S, long long sS, const float* Theta, const float* X, const float* lam,
+                             const float* GX, int B, int D, float* Gb, float* trh_part, int nblk,
+                             float* scratch, cudaStream_t st);
+size_t chol_scratch_floats(int B, int D);
+int chol_factor(float* A, int B, int D, float shift, const float* shift_dev, float* logdet, float* scratch,
+                cudaStream_t st);
+const int* chol_fail_flags(float* scratch, int B, int D);
+int chol_inverse(const float* Lf, int B, int D, float* W, float* Ainv, float alpha, const float* E1,
+                 long long sE1, float beta, float* scratch, cudaStream_t st);
+int launch_copy_shift(const float* src, long long sSrc, int B, int D, float shift, const float* shift_dev,
+                      float* dst, cudaStream_t st);
+int launch_add_diag(float* S, int B, int D, const float* add_dev, cudaStream_t st);
 
 // ---- elementwise / reductions ---------------------------------------------------------------
 int elem_blocks_per_graph(int D);

@@ -64,6 +64,15 @@ class ConditionedCovariance:
         S = _f32c(S, "S").clone()
         B, D, _ = S.shape
         lib = _lib.load()
+        self.S = S
+        if D > lib.uglad_small_d_max():
+            # large-D path: no eigendecomposition is kept (theta_0 comes from a Cholesky inverse)
+            self.wS = self.VtS = self.info = None
+            if repair:
+                scratch = torch.empty(lib.uglad_condition_scratch_floats(B, D), device=S.device, dtype=torch.float32)
+                check(lib.uglad_condition_covariance(_ptr(S), B, D, float(offset), None, None, None, _ptr(scratch),
+                                                     _stream(S)), "uglad_condition_covariance")
+            return
         self.wS = torch.empty(B, D, device=S.device, dtype=torch.float32)
         self.VtS = torch.empty(B, D, D, device=S.device, dtype=torch.float32)
         self.info = torch.empty(B, 4, device=S.device, dtype=torch.float32)
@@ -76,7 +85,6 @@ class ConditionedCovariance:
         else:
             check(lib.uglad_eigh(_ptr(S), B, D, 1, _ptr(self.wS), _ptr(self.VtS), _ptr(self.info),
                                  _ptr(scratch), _stream(S)), "uglad_eigh")
-        self.S = S
 
 
 def _eig_of(S: torch.Tensor) -> ConditionedCovariance:
@@ -141,7 +149,7 @@ class GladFunction(torch.autograd.Function):
         # previous epoch of the same fit) seeds the eigensolver; see uglad_glad_forward.
         wkey = (B, D, L, H, init_diag, S.device.index)
         warm = _warm.get(wkey) if warm_start_enabled else None
-        eig = _eig_of(S) if init_diag == 0 else None
+        eig = _eig_of(S) if (init_diag == 0 and D <= lib.uglad_small_d_max()) else None
         wS, VtS = (eig.wS, eig.VtS) if eig is not None else (None, None)
         st = _stream(S)
         if world == 1:
