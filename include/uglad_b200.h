@@ -116,11 +116,20 @@ int uglad_glasso_loss(const float* theta, const float* S, int B, int D, int S_ba
 unsigned long long uglad_launch_count(void);
 int uglad_profile(int enable, double* total_ms, unsigned long long* launches);
 
-/* developer knobs used by the tuning scripts: "eig_lp" (lanes per column pair, 0 = auto),
- * "eig_keepg" (-1 auto / 0 / 1: keep A + sigma I in a second shared-memory buffer).        */
+/* developer knobs used by the tuning scripts and tests: "eig_lp" (lanes per column pair, 0 = auto),
+ * "eig_keepg" (-1 auto / 0 / 1: keep A + sigma I in a second shared-memory buffer),
+ * "small_d_max" (threshold between the eigensolver path and the large-D path, <= 232),
+ * "use_tc" (1: tcgen05 3xTF32 products in the large-D path, 0: FP32 SIMT products),
+ * "tc_bn" (tile width of the tcgen05 kernel: 0 auto / 64 / 112 / 128).                      */
 int uglad_tune(const char* key, int value);
 
 /* building blocks exported for the parity tests */
+/* the tcgen05 3xTF32 product of the large-D path on plain operands:
+ * C[b] = alpha A[b] B[b]^T + beta E1[b] + diag I, A [batch][M][K], B [batch][N][K], C / E1 [batch][M][N]
+ * (E1 may be NULL).  scratch: uglad_tc_gemm_scratch_floats floats (the hi/lo split operands).   */
+size_t uglad_tc_gemm_scratch_floats(int M, int N, int K, int batch);
+int uglad_tc_gemm(const float* A, const float* B, const float* E1, float* C, int M, int N, int K, int batch,
+                  float alpha, float beta, float diag, float* scratch, void* stream);
 int uglad_z_update(const float* X, const float* S, const float* theta_prev, const float* params,
                    int H, int B, int D, float* Z, float* normf_out, float* scratch, void* stream);
 

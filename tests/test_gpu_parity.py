@@ -264,16 +264,51 @@ def test_size_independent_properties_at_full_size(dev):
 
 
 # ---- large-D path (Newton-Schulz as dense products + blocked Cholesky) ---------------------------
-@pytest.fixture
-def force_large_path():
+@pytest.fixture(params=[1, 0], ids=["tcgen05", "simt"])
+def force_large_path(request):
     """Lower the eigensolver/large-D threshold to 0 so that the large-D kernels run on the small
-    golden problems too (the threshold only selects the algorithm, never the result)."""
+    golden problems too (the threshold only selects the algorithm, never the result); both
+    product back-ends: tcgen05 3xTF32 (the default) and the FP32 SIMT kernel."""
     from uglad_b200 import ops
     ops.tune("small_d_max", 0)
+    ops.tune("use_tc", request.param)
     ops.reset_warm_start()
     yield
     ops.tune("small_d_max", 232)
+    ops.tune("use_tc", 1)
     ops.reset_warm_start()
+
+
+@pytest.mark.parametrize("M,N,K,batch,bn", [
+    (128, 128, 32, 1, 0), (100, 100, 100, 3, 0), (7, 5, 3, 2, 0), (200, 200, 200, 2, 0), (130, 70, 45, 2, 64),
+    (300, 260, 129, 1, 112), (256, 256, 256, 1, 128), (1000, 1000, 1000, 1, 0), (100, 100, 100, 300, 0)])
+def test_tcgen05_3xtf32_gemm(dev, M, N, K, batch, bn):
+    """C = alpha A B^T + beta E1 + diag I on the tensor pipe against float64 numpy: FP32-class
+    accuracy (3xTF32), ragged edges, batches larger than the SM count, every tile width."""
+    import ctypes as C
+    from uglad_b200 import _lib, ops
+    lib = _lib.load()
+    ops.tune("tc_bn", bn)
+    try:
+        rng = np.random.default_rng(M * 7 + N)
+        A = rng.standard_normal((batch, M, K)).astype(np.float32)
+        B = rng.standard_normal((batch, N, K)).astype(np.float32)
+        E = rng.standard_normal((batch, M, N)).astype(np.float32)
+        ref = 0.75 * np.einsum("bmk,bnk->bmn", A.astype(np.float64), B.astype(np.float64)) - 0.5 * E
+        ref[:, np.arange(min(M, N)), np.arange(min(M, N))] += 2.0
+        dA, dB, dE = (torch.tensor(x, device=dev) for x in (A, B, E))
+        out = torch.empty(batch, M, N, device=dev)
+        scratch = torch.empty(lib.uglad_tc_gemm_scratch_floats(M, N, K, batch), device=dev)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        rc = lib.uglad_tc_gemm(dA.data_ptr(), dB.data_ptr(), dE.data_ptr(), out.data_ptr(), M, N, K, batch,
+                               0.75, -0.5, 2.0, scratch.data_ptr(), st)
+        assert rc == 0, lib.uglad_last_error().decode()
+        torch.cuda.synchronize()
+        got = out.cpu().numpy().astype(np.float64)
+        scale = np.sqrt(K)  # |a||b| row-norm scale of the entries
+        assert np.abs(got - ref).max() < 4e-6 * scale * 4, np.abs(got - ref).max()
+    finally:
+        ops.tune("tc_bn", 0)
 
 
 @pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])

@@ -460,7 +460,15 @@ int uglad_tune(const char* key, int value) {
     g_small_d_max = value;
     return 0;
   }
+  if (!ns_tune(key, value)) return 0;
   return eig_small_tune(key, value);
+}
+
+size_t uglad_tc_gemm_scratch_floats(int M, int N, int K, int batch) { return tc_gemm_plain_scratch_floats(M, N, K, batch); }
+int uglad_tc_gemm(const float* A, const float* Bm, const float* E1, float* C, int M, int N, int K, int batch,
+                  float alpha, float beta, float diag, float* scratch, void* stream) {
+  if (!A || !Bm || !C || !scratch || M <= 0 || N <= 0 || K <= 0 || batch <= 0) { set_error("tc_gemm: bad arguments"); return 1; }
+  return tc_gemm_plain(A, Bm, E1, C, M, N, K, batch, alpha, beta, diag, scratch, (cudaStream_t)stream);
 }
 
 int uglad_z_update(const float* X, const float* S, const float* theta_prev, const float* params,

@@ -1,0 +1,468 @@
+// Batched 3xTF32 GEMM on the 5th-generation tensor cores (sm_100a): C = epi(A * B^T).
+//
+// Every operand is a "split" matrix: two FP32 arrays hi + lo with hi = tf32(x) (low 13 mantissa
+// bits zero) and lo = x - hi (exact), so x = hi + lo carries full FP32 precision and
+//   A B^T  ~=  A_hi B_hi^T + A_lo B_hi^T + A_hi B_lo^T          (error ~2^-21 |A||B|, FP32 accumulate)
+// which is what the 1e-4 parity budget on theta after 15 unrolled layers needs (single-pass TF32
+// is 1e-3).  Both operands are K-major (row-major [rows][K]); the callers only ever multiply by
+// symmetric matrices or provide the transpose explicitly, so B^T costs nothing.
+//
+// Structure (persistent, warp-specialised, one CTA per SM):
+//   warp 0   : TMA producer -- cp.async.bulk.tensor.3d of the four 32-float-wide K slabs
+//              (A_hi, A_lo: 128 rows; B_hi, B_lo: BN rows), 128B swizzle, mbarrier complete_tx
+//   warp 1   : MMA issuer   -- one lane issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8), three
+//              operand pairings per K granule, accumulating in TMEM; tcgen05.commit frees the slab
+//   warps 2-5: epilogue     -- tcgen05.ld of the accumulator (two TMEM stages, so the next tile's
+//              MMAs overlap), alpha/beta/diag epilogue, hi/lo split, vectorised stores
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+#include "kernels.cuh"
+
+namespace uglad {
+
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 32;                 // floats per K slab = one 128-byte swizzle row
+constexpr int A_BYTES = BM * BK * 4;   // 16 KB
+constexpr int THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (int spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && (spin & 1023) == 1023) {  // a lost arrival must fault, never hang the GPU
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000LL) asm volatile("trap;");
+    }
+  }
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand slab: rows of 128 bytes, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                   // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;         // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                   // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                   // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = (BN <= 64) ? 4 : 3;
+  static constexpr int TMEM_COLS = (BN <= 64) ? 128 : 256;  // two accumulator stages
+  static constexpr int ACC_STRIDE = TMEM_COLS / 2;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  // kind::tf32, FP32 accumulate, K-major A and B, M = 128, N = BN
+  static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+};
+
+}  // namespace tc
+
+struct TcParams {
+  int M, N, K, batch, tiles_m, tiles_n;
+  float alpha, beta, diag;
+  const float* alpha_dev;
+  const float* E1_hi;
+  const float* E1_lo;   // null: E1 is a plain FP32 matrix
+  long long sE1;
+  int lde1;
+  float* C_hi;
+  float* C_lo;          // null: C is written as plain FP32
+  long long sC;
+  int ldc;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(tc::THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+               const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, TcParams p) {
+  using C = tc::Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = tc::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;                 // 128B swizzle needs 1024-byte alignment
+  uint8_t* smem = smem_raw + (base - raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  const uint32_t bar0 = base + C::STAGES * C::STAGE_BYTES;
+  // barrier slots: full[STAGES] | empty[STAGES] | tmem_full[2] | tmem_empty[2] | tmem base address
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * C::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * C::STAGES + 2 + a); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * C::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmAh); tc::tma_prefetch_desc(&tmAl);
+    tc::tma_prefetch_desc(&tmBh); tc::tma_prefetch_desc(&tmBl);
+    for (int s = 0; s < C::STAGES; ++s) { tc::mbar_init(full_bar(s), 1); tc::mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { tc::mbar_init(tfull_bar(a), 1); tc::mbar_init(tempty_bar(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32((const void*)tmem_slot)), "r"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_batch = p.tiles_m * p.tiles_n;
+  const int total_tiles = tiles_per_batch * p.batch;
+  const int num_kb = (p.K + tc::BK - 1) / tc::BK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_batch, r = tile - b * tiles_per_batch;
+        const int tm = r / p.tiles_n, tn = r - tm * p.tiles_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          tc::mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = base + stage * C::STAGE_BYTES;
+          tc::mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          tc::tma_load_3d(sa, &tmAh, full_bar(stage), kb * tc::BK, tm * tc::BM, b);
+          tc::tma_load_3d(sa + tc::A_BYTES, &tmAl, full_bar(stage), kb * tc::BK, tm * tc::BM, b);
+          tc::tma_load_3d(sa + 2 * tc::A_BYTES, &tmBh, full_bar(stage), kb * tc::BK, tn * BN, b);
+          tc::tma_load_3d(sa + 2 * tc::A_BYTES + C::B_BYTES, &tmBl, full_bar(stage), kb * tc::BK, tn * BN, b);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        tc::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * C::ACC_STRIDE;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          tc::mbar_wait(full_bar(stage), phase);
+          tc::tc_fence_after();
+          const uint32_t sa = base + stage * C::STAGE_BYTES;
+          const uint64_t dAh = tc::umma_desc(sa), dAl = tc::umma_desc(sa + tc::A_BYTES);
+          const uint64_t dBh = tc::umma_desc(sa + 2 * tc::A_BYTES), dBl = tc::umma_desc(sa + 2 * tc::A_BYTES + C::B_BYTES);
+          const int krem = p.K - kb * tc::BK;
+          const int ngran = krem >= tc::BK ? 4 : (krem + 7) >> 3;   // K granules of 8 that hold data
+          for (int g = 0; g < ngran; ++g) {
+            const uint64_t adv = (uint64_t)(g * 2);                 // 32 bytes >> 4 inside the swizzle row
+            tc::umma_tf32(tmem_d, dAl + adv, dBh + adv, C::IDESC, (kb | g) != 0);
+            tc::umma_tf32(tmem_d, dAh + adv, dBl + adv, C::IDESC, 1u);
+            tc::umma_tf32(tmem_d, dAh + adv, dBh + adv, C::IDESC, 1u);
+          }
+          tc::umma_commit(empty_bar(stage));
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc::umma_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    int acc = 0; uint32_t acc_phase = 0;
+    const bool vec_c = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C_hi) & 15) == 0) &&
+                       (p.C_lo == nullptr || (reinterpret_cast<uintptr_t>(p.C_lo) & 15) == 0) && (p.sC % 4 == 0);
+    const bool vec_e = p.E1_hi != nullptr && (p.lde1 % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.E1_hi) & 15) == 0) &&
+                       (p.E1_lo == nullptr || (reinterpret_cast<uintptr_t>(p.E1_lo) & 15) == 0) && (p.sE1 % 4 == 0);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_batch, r = tile - b * tiles_per_batch;
+      const int tm = r / p.tiles_n, tn = r - tm * p.tiles_n;
+      tc::mbar_wait(tfull_bar(acc), acc_phase);
+      tc::tc_fence_after();
+      const int row = tm * tc::BM + q * 32 + lane;
+      const float alpha = p.alpha_dev ? p.alpha * p.alpha_dev[b] : p.alpha;
+      float* Ch = p.C_hi + (size_t)b * p.sC + (size_t)row * p.ldc;
+      float* Cl = p.C_lo ? p.C_lo + (size_t)b * p.sC + (size_t)row * p.ldc : nullptr;
+      const float* Eh = p.E1_hi ? p.E1_hi + (size_t)b * p.sE1 + (size_t)row * p.lde1 : nullptr;
+      const float* El = p.E1_lo ? p.E1_lo + (size_t)b * p.sE1 + (size_t)row * p.lde1 : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::ACC_STRIDE + c0, v);
+        if (row < p.M) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int col = tn * BN + c0 + j;
+            if (col >= p.N) break;
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = alpha * __uint_as_float(v[j + e]);
+            const bool full4 = col + 3 < p.N;
+            if (Eh) {
+              if (full4 && vec_e) {
+                const float4 eh = *reinterpret_cast<const float4*>(Eh + col);
+                o[0] = fmaf(p.beta, eh.x, o[0]); o[1] = fmaf(p.beta, eh.y, o[1]);
+                o[2] = fmaf(p.beta, eh.z, o[2]); o[3] = fmaf(p.beta, eh.w, o[3]);
+                if (El) {
+                  const float4 el = *reinterpret_cast<const float4*>(El + col);
+                  o[0] = fmaf(p.beta, el.x, o[0]); o[1] = fmaf(p.beta, el.y, o[1]);
+                  o[2] = fmaf(p.beta, el.z, o[2]); o[3] = fmaf(p.beta, el.w, o[3]);
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (col + e < p.N) {
+                    float ev = Eh[col + e];
+                    if (El) ev += El[col + e];
+                    o[e] = fmaf(p.beta, ev, o[e]);
+                  }
+              }
+            }
+            if (p.diag != 0.f) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (col + e == row) o[e] += p.diag;
+            }
+            if (Cl) {
+              float h[4], l[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                uint32_t hb;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(o[e]));
+                h[e] = __uint_as_float(hb);
+                l[e] = o[e] - h[e];
+              }
+              if (full4 && vec_c) {
+                *reinterpret_cast<float4*>(Ch + col) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(Cl + col) = make_float4(l[0], l[1], l[2], l[3]);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (col + e < p.N) { Ch[col + e] = h[e]; Cl[col + e] = l[e]; }
+              }
+            } else {
+              if (full4 && vec_c) {
+                *reinterpret_cast<float4*>(Ch + col) = make_float4(o[0], o[1], o[2], o[3]);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (col + e < p.N) Ch[col + e] = o[e];
+              }
+            }
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc::tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor maps (cached: the operands live in a handful of fixed scratch matrices)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr; int rows, cols, ld, batch, box_rows; long long stride;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && batch == o.batch &&
+           box_rows == o.box_rows && stride == o.stride;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    auto mix = [&](size_t v) { h ^= v + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2); };
+    mix(k.rows); mix(k.cols); mix(k.ld); mix(k.batch); mix(k.box_rows); mix((size_t)k.stride);
+    return h;
+  }
+};
+static std::mutex g_map_mu;
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+// tensor map of a batched row-major matrix [batch][rows][cols] (row stride ld, batch stride `stride`
+// floats), box = 32 columns x box_rows rows x 1, 128-byte swizzle, zero fill outside the matrix
+static int get_map(const float* ptr, int rows, int cols, int ld, int batch, long long stride, int box_rows,
+                   CUtensorMap* out) {
+  const MapKey key{ptr, rows, cols, ld, batch, box_rows, stride};
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) { *out = it->second; return 0; }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return 1; }
+  const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+  const cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(batch > 1 ? stride : (long long)ld * rows) * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)tc::BK, (cuuint32_t)box_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap m;
+  const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for rows=%d cols=%d ld=%d batch=%d", (int)r, rows, cols, ld, batch);
+    return 1;
+  }
+  if (g_maps.size() > 4096) g_maps.clear();
+  g_maps.emplace(key, m);
+  *out = m;
+  return 0;
+}
+void tc_forget_maps() {
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  g_maps.clear();
+}
+
+static int g_num_sms = 0;
+static int g_tc_bn = 0;  // 0 = auto
+int tc_tune_bn(int bn) { g_tc_bn = bn; return 0; }
+
+template <int BN>
+static int launch_tc(const TcGemm& g, int batch, cudaStream_t st) {
+  using C = tc::Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    UGLAD_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    attr_set = true;
+  }
+  CUtensorMap mAh, mAl, mBh, mBl;
+  if (get_map(g.A_hi, g.M, g.K, g.lda, batch, g.sA, tc::BM, &mAh)) return 1;
+  if (get_map(g.A_lo, g.M, g.K, g.lda, batch, g.sA, tc::BM, &mAl)) return 1;
+  if (get_map(g.B_hi, g.N, g.K, g.ldb, batch, g.sB, BN, &mBh)) return 1;
+  if (get_map(g.B_lo, g.N, g.K, g.ldb, batch, g.sB, BN, &mBl)) return 1;
+  TcParams p;
+  p.M = g.M; p.N = g.N; p.K = g.K; p.batch = batch;
+  p.tiles_m = (g.M + tc::BM - 1) / tc::BM;
+  p.tiles_n = (g.N + BN - 1) / BN;
+  p.alpha = g.alpha; p.beta = g.beta; p.diag = g.diag; p.alpha_dev = g.alpha_dev;
+  p.E1_hi = g.E1_hi; p.E1_lo = g.E1_lo; p.sE1 = g.sE1; p.lde1 = g.lde1;
+  p.C_hi = g.C_hi; p.C_lo = g.C_lo; p.sC = g.sC; p.ldc = g.ldc;
+  const long long total = (long long)p.tiles_m * p.tiles_n * batch;
+  if (g_num_sms == 0) {
+    int dev = 0;
+    UGLAD_CUDA(cudaGetDevice(&dev));
+    UGLAD_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int grid = (int)(total < g_num_sms ? total : g_num_sms);
+  tc_gemm_kernel<BN><<<grid, tc::THREADS, C::SMEM, st>>>(mAh, mAl, mBh, mBl, p);
+  UGLAD_CHECK_LAUNCH("tc_gemm_kernel");
+  return 0;
+}
+
+bool tc_gemm_supported(const TcGemm& g) {
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return g.lda % 4 == 0 && g.ldb % 4 == 0 && g.sA % 4 == 0 && g.sB % 4 == 0 && al16(g.A_hi) && al16(g.A_lo) &&
+         al16(g.B_hi) && al16(g.B_lo) && g.M > 0 && g.N > 0 && g.K > 0;
+}
+
+int launch_tc_gemm(const TcGemm& g, int batch, cudaStream_t st) {
+  if (!tc_gemm_supported(g)) { set_error("tc_gemm: operands must be 16-byte aligned with ld %% 4 == 0"); return 1; }
+  if (batch <= 0) return 0;
+  if (g_num_sms == 0) {
+    int dev = 0;
+    UGLAD_CUDA(cudaGetDevice(&dev));
+    UGLAD_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  int bn = g_tc_bn;
+  if (bn == 0) {
+    // narrowest tile that covers N in one pass; for wide N pick the width that fills the SMs best
+    if (g.N <= 64) bn = 64;
+    else if (g.N <= 112) bn = 112;
+    else if (g.N <= 128) bn = 128;
+    else {
+      const long long tm = (g.M + tc::BM - 1) / tc::BM;
+      double best = 1e300;
+      const int cand[3] = {128, 112, 64};
+      for (int c : cand) {
+        const long long tiles = tm * ((g.N + c - 1) / c) * batch;
+        const long long waves = (tiles + g_num_sms - 1) / g_num_sms;
+        const double cost = (double)waves * (c + 40);   // MMA time ~ BN, fixed per-tile overhead
+        if (cost < best) { best = cost; bn = c; }
+      }
+    }
+  }
+  switch (bn) {
+    case 64: return launch_tc<64>(g, batch, st);
+    case 112: return launch_tc<112>(g, batch, st);
+    case 128: return launch_tc<128>(g, batch, st);
+  }
+  set_error("tc_gemm: unsupported tile width %d", bn);
+  return 1;
+}
+
+}  // namespace uglad

@@ -65,6 +65,24 @@ struct GemmArgs {
 int launch_gemm(const GemmArgs& g, int batch, cudaStream_t st);       // FP32 SIMT kernel
 int launch_gemm_auto(const GemmArgs& g, int batch, cudaStream_t st);  // tcgen05 3xTF32 when the shape allows
 
+// ---- tcgen05 3xTF32 GEMM on split (hi + lo) operands: C = alpha A B^T + beta E1 + diag I ------
+struct TcGemm {
+  const float* A_hi = nullptr; const float* A_lo = nullptr;   // [batch][M][K], row stride lda
+  const float* B_hi = nullptr; const float* B_lo = nullptr;   // [batch][N][K], row stride ldb
+  int M = 0, N = 0, K = 0, lda = 0, ldb = 0;
+  long long sA = 0, sB = 0;
+  float alpha = 1.f, beta = 0.f, diag = 0.f;
+  const float* alpha_dev = nullptr;                           // per-batch scalar, stride 1
+  const float* E1_hi = nullptr; const float* E1_lo = nullptr; // E1_lo null: plain FP32 addend
+  long long sE1 = 0; int lde1 = 0;
+  float* C_hi = nullptr; float* C_lo = nullptr;               // C_lo null: plain FP32 output
+  long long sC = 0; int ldc = 0;
+};
+bool tc_gemm_supported(const TcGemm& g);
+int launch_tc_gemm(const TcGemm& g, int batch, cudaStream_t st);
+int tc_tune_bn(int bn);
+void tc_forget_maps();
+
 // ---- large-D path: Newton-Schulz in GEMM form (ns_large.cu), blocked Cholesky (chol_large.cu)
 size_t ns_scratch_floats(int B, int D);
 int ns_scratch_init(float* scratch, int B, int D, cudaStream_t st);
@@ -73,6 +91,19 @@ int ns_theta_update_forward(const float* S, long long sS, const float* Theta, co
 int ns_theta_update_backward(const float* S, long long sS, const float* Theta, const float* X, const float* lam,
                              const float* GX, int B, int D, float* Gb, float* trh_part, int nblk,
                              float* scratch, cudaStream_t st);
+int ns_tune(const char* key, int value);   // "use_tc": 1 (default) tcgen05 3xTF32 products, 0 FP32 SIMT products
+size_t ns_tc_scratch_floats(int B, int D);
+int ns_tc_scratch_init(float* scratch, int B, int D, cudaStream_t st);
+int ns_tc_theta_update_forward(const float* S, long long sS, const float* Theta, const float* lam, int B, int D,
+                               float* X, float* scratch, cudaStream_t st);
+int ns_tc_theta_update_backward(const float* S, long long sS, const float* Theta, const float* X, const float* lam,
+                                const float* GX, int B, int D, float* Gb, float* trh_part, int nblk,
+                                float* scratch, cudaStream_t st);
+int launch_tcs_split(const float* src, long long sSrc, int B, int rows, int cols, int ld, int ldp, float* hi, float* lo,
+                     cudaStream_t st);
+int tc_gemm_plain(const float* A, const float* Bm, const float* E1, float* C, int M, int N, int K, int batch,
+                  float alpha, float beta, float diag, float* scratch, cudaStream_t st);
+size_t tc_gemm_plain_scratch_floats(int M, int N, int K, int batch);
 size_t chol_scratch_floats(int B, int D);
 int chol_factor(float* A, int B, int D, float shift, const float* shift_dev, float* logdet, float* scratch,
                 cudaStream_t st);

@@ -11,6 +11,7 @@
 //   H = Q/2 = dL/d(b b + 4/lam I) ;  Gb = b (H + H^T) - GX/2 ;  tr(H) feeds dL/dlam.
 // Every product goes through mm(): the tcgen05 3xTF32 kernel when the shape allows it,
 // the FP32 SIMT kernel otherwise.
+#include <string.h>
 #include "kernels.cuh"
 
 namespace uglad {
@@ -172,9 +173,21 @@ struct NsBuf {
 };
 static inline size_t al4(size_t x) { return (x + 3) & ~(size_t)3; }
 
-size_t ns_scratch_floats(int B, int D) {
+static int g_use_tc = 1;
+int ns_tune(const char* key, int value) {
+  if (!strcmp(key, "use_tc")) { g_use_tc = value ? 1 : 0; return 0; }
+  if (!strcmp(key, "tc_bn")) return tc_tune_bn(value);
+  return 1;
+}
+
+static size_t ns_simt_scratch_floats(int B, int D) {
   const size_t n2 = (size_t)B * D * D;
   return 8 * al4(n2) + al4(3 * (size_t)B) + al4((size_t)B * elem_blocks_per_graph(D)) + al4(B);
+}
+// one region serves both product back-ends (the "use_tc" knob may flip between calls)
+size_t ns_scratch_floats(int B, int D) {
+  const size_t a = ns_simt_scratch_floats(B, D), b = ns_tc_scratch_floats(B, D);
+  return a > b ? a : b;
 }
 static NsBuf ns_carve(float* scratch, int B, int D) {
   NsBuf s;
@@ -188,7 +201,7 @@ static NsBuf ns_carve(float* scratch, int B, int D) {
 int ns_scratch_init(float* scratch, int B, int D, cudaStream_t st) {
   NsBuf s = ns_carve(scratch, B, D);
   UGLAD_CUDA(cudaMemsetAsync(s.counter, 0, (size_t)B * sizeof(unsigned), st));
-  return 0;
+  return ns_tc_scratch_init(scratch, B, D, st);
 }
 
 struct MM {
@@ -213,6 +226,7 @@ static int mm(const MM& m, int B, int D, cudaStream_t st) {
 
 int ns_theta_update_forward(const float* S, long long sS, const float* Theta, const float* lam, int B, int D,
                             float* X, float* scratch, cudaStream_t st) {
+  if (g_use_tc) return ns_tc_theta_update_forward(S, sS, Theta, lam, B, D, X, scratch, st);
   const NsBuf s = ns_carve(scratch, B, D);
   const int n = D * D;
   const dim3 grid(elem_blocks_per_graph(D), B);
@@ -244,6 +258,7 @@ int ns_theta_update_forward(const float* S, long long sS, const float* Theta, co
 int ns_theta_update_backward(const float* S, long long sS, const float* Theta, const float* X, const float* lam,
                              const float* GX, int B, int D, float* Gb, float* trh_part, int nblk,
                              float* scratch, cudaStream_t st) {
+  if (g_use_tc) return ns_tc_theta_update_backward(S, sS, Theta, X, lam, GX, B, D, Gb, trh_part, nblk, scratch, st);
   const NsBuf s = ns_carve(scratch, B, D);
   const int n = D * D;
   const dim3 grid(elem_blocks_per_graph(D), B);

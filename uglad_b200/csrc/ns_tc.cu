@@ -1,0 +1,373 @@
+// Large-D theta update on the tensor pipe: the Newton-Schulz chain of ns_large.cu with every
+// product issued as a tcgen05 3xTF32 GEMM (gemm_tc.cu).  All intermediates are "split" matrices
+// (hi = tf32(x), lo = x - hi; [B][D][ldp] with ldp = D rounded up to 4 so that TMA row strides are
+// 16-byte multiples).  The GEMM computes X Y^T; every right-hand operand of the chain is
+// symmetric (a polynomial in b, or A / Q / H + H^T of the backward), or antisymmetric
+// (W = A Q - Q A, where the sign flips), so no transposes are ever materialised:
+//   forward   A = b b ; Y1 = (A/n) T0 ; { T = (3I - Z Y)/2 ; Y <- Y T ; Z <- T Z } ; X = (sqrt(n) Y T - b)/2
+//   backward  B3 = 3I - A A ; QB = Q B3 ; W = A Q - Q A ; Q <- (QB - A W)/2 = (QB + A W^T)/2 ; A <- A B3 / 2
+#include "kernels.cuh"
+
+namespace uglad {
+
+constexpr int TCS_THREADS = 256;
+
+struct SplitMat { float* hi; float* lo; };
+
+__device__ __forceinline__ void split_tf32(float v, float& h, float& l) {
+  uint32_t hb;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+  h = __uint_as_float(hb);
+  l = v - h;
+}
+
+__device__ __forceinline__ void tcs_finish_norm(float tot, float* part, unsigned* counter, float* scal, int B,
+                                                double* redd, bool* s_last) {
+  const int b = blockIdx.y, nb = gridDim.x;
+  if (threadIdx.x == 0) {
+    part[(size_t)b * nb + blockIdx.x] = tot;
+    __threadfence();
+    *s_last = (atomicAdd(counter + b, 1u) == (unsigned)nb - 1u);
+  }
+  __syncthreads();
+  if (*s_last) {
+    __threadfence();
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) s += (double)((volatile float*)part)[(size_t)b * nb + i];
+    s = block_sum_d(s, redd);
+    if (threadIdx.x == 0) {
+      const double n = sqrt(s);
+      scal[b] = (float)n;
+      scal[B + b] = (float)(1.0 / n);
+      scal[2 * B + b] = (float)sqrt(n);
+      counter[b] = 0u;
+    }
+  }
+}
+
+// b = S/lam - Theta  (dense in, split out)
+__global__ void __launch_bounds__(TCS_THREADS) tcs_build_b_kernel(const float* __restrict__ S, long long sS,
+                                                                 const float* __restrict__ Theta,
+                                                                 const float* __restrict__ lam, int D, int ldp,
+                                                                 float* __restrict__ bh, float* __restrict__ bl) {
+  const float il = 1.f / lam[0];
+  const int n = D * D;
+  const float* Sb = S + (size_t)blockIdx.y * sS;
+  const size_t base = (size_t)blockIdx.y * n, pbase = (size_t)blockIdx.y * D * ldp;
+  for (int i = blockIdx.x * TCS_THREADS + threadIdx.x; i < n; i += gridDim.x * TCS_THREADS) {
+    const int r = i / D, c = i - r * D;
+    float h, l;
+    split_tf32(fmaf(il, Sb[i], -Theta[base + i]), h, l);
+    bh[pbase + (size_t)r * ldp + c] = h;
+    bl[pbase + (size_t)r * ldp + c] = l;
+  }
+}
+
+// A_ii += 4/lam ; scal <- ||A||_F
+__global__ void __launch_bounds__(TCS_THREADS) tcs_diag_fro_kernel(float* __restrict__ Ah, float* __restrict__ Al,
+                                                                  const float* __restrict__ lam, int D, int ldp,
+                                                                  float* part, unsigned* counter, float* scal, int B) {
+  __shared__ float red[32];
+  __shared__ double redd[32];
+  __shared__ bool s_last;
+  const float c4 = 4.f / lam[0];
+  const int n = D * D;
+  const size_t pbase = (size_t)blockIdx.y * D * ldp;
+  float acc = 0.f;
+  for (int i = blockIdx.x * TCS_THREADS + threadIdx.x; i < n; i += gridDim.x * TCS_THREADS) {
+    const int r = i / D, c = i - r * D;
+    const size_t o = pbase + (size_t)r * ldp + c;
+    float v = Ah[o] + Al[o];
+    if (r == c) {
+      v += c4;
+      float h, l;
+      split_tf32(v, h, l);
+      Ah[o] = h;
+      Al[o] = l;
+    }
+    acc = fmaf(v, v, acc);
+  }
+  const float tot = block_sum(acc, red);
+  tcs_finish_norm(tot, part, counter, scal, B, redd, &s_last);
+}
+
+// Z1 = T0 = (3I - A/n)/2
+__global__ void __launch_bounds__(TCS_THREADS) tcs_t0_kernel(const float* __restrict__ Ah, const float* __restrict__ Al,
+                                                            const float* __restrict__ scal, int B, int D, int ldp,
+                                                            float* __restrict__ Zh, float* __restrict__ Zl) {
+  const int n = D * D;
+  const size_t pbase = (size_t)blockIdx.y * D * ldp;
+  const float hf = -0.5f * scal[B + blockIdx.y];
+  for (int i = blockIdx.x * TCS_THREADS + threadIdx.x; i < n; i += gridDim.x * TCS_THREADS) {
+    const int r = i / D, c = i - r * D;
+    const size_t o = pbase + (size_t)r * ldp + c;
+    float h, l;
+    split_tf32(fmaf(hf, Ah[o] + Al[o], (r == c) ? 1.5f : 0.f), h, l);
+    Zh[o] = h;
+    Zl[o] = l;
+  }
+}
+
+// backward prologue: b = S/lam - Theta (split) ; R = 2X + b (plain, padded layout) ; scal <- ||R||_F
+__global__ void __launch_bounds__(TCS_THREADS) tcs_build_r_kernel(const float* __restrict__ S, long long sS,
+                                                                 const float* __restrict__ Theta,
+                                                                 const float* __restrict__ X,
+                                                                 const float* __restrict__ lam, int D, int ldp,
+                                                                 float* __restrict__ bh, float* __restrict__ bl,
+                                                                 float* __restrict__ R, float* part, unsigned* counter,
+                                                                 float* scal, int B) {
+  __shared__ float red[32];
+  __shared__ double redd[32];
+  __shared__ bool s_last;
+  const float il = 1.f / lam[0];
+  const int n = D * D;
+  const float* Sb = S + (size_t)blockIdx.y * sS;
+  const size_t base = (size_t)blockIdx.y * n, pbase = (size_t)blockIdx.y * D * ldp;
+  float acc = 0.f;
+  for (int i = blockIdx.x * TCS_THREADS + threadIdx.x; i < n; i += gridDim.x * TCS_THREADS) {
+    const int r = i / D, c = i - r * D;
+    const size_t o = pbase + (size_t)r * ldp + c;
+    const float bv = fmaf(il, Sb[i], -Theta[base + i]);
+    const float rv = fmaf(2.f, X[base + i], bv);
+    float h, l;
+    split_tf32(bv, h, l);
+    bh[o] = h;
+    bl[o] = l;
+    R[o] = rv;
+    acc = fmaf(rv, rv, acc);
+  }
+  const float tot = block_sum(acc, red);
+  tcs_finish_norm(tot, part, counter, scal, B, redd, &s_last);
+}
+
+// A = R/r (R sits in Ah, plain) ; Q = (GX/2)/r ; both split
+__global__ void __launch_bounds__(TCS_THREADS) tcs_scale_aq_kernel(float* __restrict__ Ah, float* __restrict__ Al,
+                                                                  const float* __restrict__ GX,
+                                                                  const float* __restrict__ scal, int B, int D, int ldp,
+                                                                  float* __restrict__ Qh, float* __restrict__ Ql) {
+  const int n = D * D;
+  const size_t base = (size_t)blockIdx.y * n, pbase = (size_t)blockIdx.y * D * ldp;
+  const float inv = scal[B + blockIdx.y];
+  for (int i = blockIdx.x * TCS_THREADS + threadIdx.x; i < n; i += gridDim.x * TCS_THREADS) {
+    const int r = i / D, c = i - r * D;
+    const size_t o = pbase + (size_t)r * ldp + c;
+    float h, l;
+    split_tf32(Ah[o] * inv, h, l);
+    Ah[o] = h;
+    Al[o] = l;
+    split_tf32(GX[base + i] * (0.5f * inv), h, l);
+    Qh[o] = h;
+    Ql[o] = l;
+  }
+}
+
+// Hs = H + H^T = (Q + Q^T)/2 (split) ; partial traces of H = Q/2.  32x32 tiles, block (32, 8).
+__global__ void tcs_hsym_kernel(const float* __restrict__ Qh, const float* __restrict__ Ql, int D, int ldp,
+                                float* __restrict__ Hh, float* __restrict__ Hl, float* trh_part, int part_stride) {
+  __shared__ float t[32][33];
+  __shared__ float red[8];
+  const size_t pbase = (size_t)blockIdx.z * D * ldp;
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int gi = bx + r, gj = by + threadIdx.x;
+    const size_t o = pbase + (size_t)gi * ldp + gj;
+    t[r][threadIdx.x] = (gi < D && gj < D) ? Qh[o] + Ql[o] : 0.f;
+  }
+  __syncthreads();
+  float tr = 0.f;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int gi = by + r, gj = bx + threadIdx.x;
+    if (gi < D && gj < D) {
+      const size_t o = pbase + (size_t)gi * ldp + gj;
+      const float q = Qh[o] + Ql[o];
+      float h, l;
+      split_tf32(0.5f * (q + t[threadIdx.x][r]), h, l);
+      Hh[o] = h;
+      Hl[o] = l;
+      if (gi == gj) tr += 0.5f * q;
+    }
+  }
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  tr = warp_sum(tr);
+  if ((tid & 31) == 0) red[tid >> 5] = tr;
+  __syncthreads();
+  if (tid == 0 && blockIdx.x == blockIdx.y) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    trh_part[(size_t)blockIdx.z * part_stride + blockIdx.x] = s;
+  }
+}
+
+// plain [B][rows][cols] (row stride ld, batch stride sSrc) -> split [B][rows][ldp]; optional transpose-free
+__global__ void __launch_bounds__(TCS_THREADS) tcs_split_kernel(const float* __restrict__ src, long long sSrc, int rows,
+                                                               int cols, int ld, int ldp, float* __restrict__ hi,
+                                                               float* __restrict__ lo) {
+  const long long n = (long long)rows * cols;
+  const float* s = src + (size_t)blockIdx.y * sSrc;
+  const size_t pbase = (size_t)blockIdx.y * rows * ldp;
+  for (long long i = (long long)blockIdx.x * TCS_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * TCS_THREADS) {
+    const int r = (int)(i / cols), c = (int)(i - (long long)r * cols);
+    float h, l;
+    split_tf32(s[(size_t)r * ld + c], h, l);
+    hi[pbase + (size_t)r * ldp + c] = h;
+    lo[pbase + (size_t)r * ldp + c] = l;
+  }
+}
+int launch_tcs_split(const float* src, long long sSrc, int B, int rows, int cols, int ld, int ldp, float* hi, float* lo,
+                     cudaStream_t st) {
+  long long blocks = ((long long)rows * cols + 2047) / 2048;
+  if (blocks > 1024) blocks = 1024;
+  if (blocks < 1) blocks = 1;
+  dim3 grid((unsigned)blocks, B);
+  tcs_split_kernel<<<grid, TCS_THREADS, 0, st>>>(src, sSrc, rows, cols, ld, ldp, hi, lo);
+  UGLAD_CHECK_LAUNCH("tcs_split_kernel");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+static inline size_t al4t(size_t x) { return (x + 3) & ~(size_t)3; }
+static inline int ldp_of(int D) { return (D + 3) & ~3; }
+
+struct TcsBuf {
+  SplitMat M[8];
+  float* scal;
+  float* part;
+  unsigned* counter;
+  int ldp;
+  long long n2p;  // floats per split half: B * D * ldp
+};
+size_t ns_tc_scratch_floats(int B, int D) {
+  const size_t n2p = al4t((size_t)B * D * ldp_of(D));
+  return 16 * n2p + al4t(3 * (size_t)B) + al4t((size_t)B * elem_blocks_per_graph(D)) + al4t(B);
+}
+static TcsBuf tcs_carve(float* scratch, int B, int D) {
+  TcsBuf s;
+  s.ldp = ldp_of(D);
+  s.n2p = (long long)al4t((size_t)B * D * s.ldp);
+  for (int i = 0; i < 8; ++i) {
+    s.M[i].hi = scratch + (size_t)(2 * i) * s.n2p;
+    s.M[i].lo = scratch + (size_t)(2 * i + 1) * s.n2p;
+  }
+  s.scal = scratch + 16 * (size_t)s.n2p;
+  s.part = s.scal + al4t(3 * (size_t)B);
+  s.counter = reinterpret_cast<unsigned*>(s.part + al4t((size_t)B * elem_blocks_per_graph(D)));
+  return s;
+}
+int ns_tc_scratch_init(float* scratch, int B, int D, cudaStream_t st) {
+  const TcsBuf s = tcs_carve(scratch, B, D);
+  UGLAD_CUDA(cudaMemsetAsync(s.counter, 0, (size_t)B * sizeof(unsigned), st));
+  return 0;
+}
+
+struct TMM {
+  SplitMat A, Bm, C;                 // C.lo null: plain output (ldc / sC given)
+  float alpha = 1.f; const float* alpha_dev = nullptr;
+  float beta = 0.f; SplitMat E1 = {nullptr, nullptr}; int lde1 = 0; long long sE1 = 0;
+  float diag = 0.f;
+  int ldc = 0; long long sC = 0;
+};
+static int tmm(const TMM& m, const TcsBuf& s, int B, int D, cudaStream_t st) {
+  TcGemm g;
+  g.A_hi = m.A.hi; g.A_lo = m.A.lo; g.B_hi = m.Bm.hi; g.B_lo = m.Bm.lo;
+  g.M = g.N = g.K = D;
+  g.lda = g.ldb = s.ldp;
+  g.sA = g.sB = (long long)D * s.ldp;
+  g.alpha = m.alpha; g.alpha_dev = m.alpha_dev; g.beta = m.beta; g.diag = m.diag;
+  g.E1_hi = m.E1.hi; g.E1_lo = m.E1.lo;
+  g.lde1 = m.lde1 ? m.lde1 : s.ldp;
+  g.sE1 = m.sE1 ? m.sE1 : (long long)D * s.ldp;
+  g.C_hi = m.C.hi; g.C_lo = m.C.lo;
+  g.ldc = m.ldc ? m.ldc : s.ldp;
+  g.sC = m.sC ? m.sC : (long long)D * s.ldp;
+  return launch_tc_gemm(g, B, st);
+}
+
+int ns_tc_theta_update_forward(const float* S, long long sS, const float* Theta, const float* lam, int B, int D,
+                               float* X, float* scratch, cudaStream_t st) {
+  const TcsBuf s = tcs_carve(scratch, B, D);
+  const dim3 grid(elem_blocks_per_graph(D), B);
+  SplitMat b = s.M[0], A = s.M[1], Z = s.M[2], T = s.M[3], Y = s.M[4], Y2 = s.M[5], Z2 = s.M[6];
+  tcs_build_b_kernel<<<grid, TCS_THREADS, 0, st>>>(S, sS, Theta, lam, D, s.ldp, b.hi, b.lo);
+  UGLAD_CHECK_LAUNCH("tcs_build_b_kernel");
+  { TMM m; m.A = b; m.Bm = b; m.C = A; if (tmm(m, s, B, D, st)) return 1; }
+  tcs_diag_fro_kernel<<<grid, TCS_THREADS, 0, st>>>(A.hi, A.lo, lam, D, s.ldp, s.part, s.counter, s.scal, B);
+  UGLAD_CHECK_LAUNCH("tcs_diag_fro_kernel");
+  tcs_t0_kernel<<<grid, TCS_THREADS, 0, st>>>(A.hi, A.lo, s.scal, B, D, s.ldp, Z.hi, Z.lo);
+  UGLAD_CHECK_LAUNCH("tcs_t0_kernel");
+  { TMM m; m.A = A; m.Bm = Z; m.C = Y; m.alpha_dev = s.scal + B; if (tmm(m, s, B, D, st)) return 1; }
+  for (int t = 1; t < UGLAD_NS_ITERS; ++t) {
+    { TMM m; m.A = Z; m.Bm = Y; m.C = T; m.alpha = -0.5f; m.diag = 1.5f; if (tmm(m, s, B, D, st)) return 1; }
+    if (t + 1 < UGLAD_NS_ITERS) {
+      { TMM m; m.A = Y; m.Bm = T; m.C = Y2; if (tmm(m, s, B, D, st)) return 1; }
+      { TMM m; m.A = T; m.Bm = Z; m.C = Z2; if (tmm(m, s, B, D, st)) return 1; }
+      SplitMat tmp = Y; Y = Y2; Y2 = tmp;
+      tmp = Z; Z = Z2; Z2 = tmp;
+    } else {
+      TMM m; m.A = Y; m.Bm = T; m.C = SplitMat{X, nullptr}; m.ldc = D; m.sC = (long long)D * D;
+      m.alpha = 0.5f; m.alpha_dev = s.scal + 2 * B; m.beta = -0.5f; m.E1 = b;
+      if (tmm(m, s, B, D, st)) return 1;
+    }
+  }
+  return 0;
+}
+
+int ns_tc_theta_update_backward(const float* S, long long sS, const float* Theta, const float* X, const float* lam,
+                                const float* GX, int B, int D, float* Gb, float* trh_part, int nblk,
+                                float* scratch, cudaStream_t st) {
+  const TcsBuf s = tcs_carve(scratch, B, D);
+  const dim3 grid(elem_blocks_per_graph(D), B);
+  SplitMat b = s.M[0], A = s.M[1], A2 = s.M[2], Q = s.M[3], Q2 = s.M[4], B3 = s.M[5], QB = s.M[6], W = s.M[7];
+  tcs_build_r_kernel<<<grid, TCS_THREADS, 0, st>>>(S, sS, Theta, X, lam, D, s.ldp, b.hi, b.lo, A.hi, s.part,
+                                                    s.counter, s.scal, B);
+  UGLAD_CHECK_LAUNCH("tcs_build_r_kernel");
+  tcs_scale_aq_kernel<<<grid, TCS_THREADS, 0, st>>>(A.hi, A.lo, GX, s.scal, B, D, s.ldp, Q.hi, Q.lo);
+  UGLAD_CHECK_LAUNCH("tcs_scale_aq_kernel");
+  for (int t = 0; t < UGLAD_NS_ITERS; ++t) {
+    { TMM m; m.A = A; m.Bm = A; m.C = B3; m.alpha = -1.f; m.diag = 3.f; if (tmm(m, s, B, D, st)) return 1; }
+    { TMM m; m.A = Q; m.Bm = B3; m.C = QB; if (tmm(m, s, B, D, st)) return 1; }
+    { TMM m; m.A = Q; m.Bm = A; m.C = W; if (tmm(m, s, B, D, st)) return 1; }
+    { TMM m; m.A = A; m.Bm = Q; m.C = W; m.beta = -1.f; m.E1 = W; if (tmm(m, s, B, D, st)) return 1; }
+    { TMM m; m.A = A; m.Bm = W; m.C = Q2; m.alpha = 0.5f; m.beta = 0.5f; m.E1 = QB; if (tmm(m, s, B, D, st)) return 1; }
+    if (t + 1 < UGLAD_NS_ITERS) {
+      TMM m; m.A = A; m.Bm = B3; m.C = A2; m.alpha = 0.5f;
+      if (tmm(m, s, B, D, st)) return 1;
+      SplitMat tmp = A; A = A2; A2 = tmp;
+    }
+    SplitMat tmp = Q; Q = Q2; Q2 = tmp;
+  }
+  {
+    UGLAD_CUDA(cudaMemsetAsync(trh_part, 0, (size_t)B * nblk * sizeof(float), st));
+    const int nt = (D + 31) / 32;
+    if (nt > nblk) { set_error("ns backward: %d trace partials do not fit %d slots", nt, nblk); return 1; }
+    dim3 g2(nt, nt, B), blk(32, 8);
+    tcs_hsym_kernel<<<g2, blk, 0, st>>>(Q.hi, Q.lo, D, s.ldp, B3.hi, B3.lo, trh_part, nblk);
+    UGLAD_CHECK_LAUNCH("tcs_hsym_kernel");
+  }
+  TMM m; m.A = b; m.Bm = B3; m.C = SplitMat{Gb, nullptr}; m.ldc = D; m.sC = (long long)D * D;
+  m.beta = -0.5f; m.E1 = SplitMat{const_cast<float*>(GX), nullptr}; m.lde1 = D; m.sE1 = (long long)D * D;
+  return tmm(m, s, B, D, st);
+}
+
+// test / building-block entry: plain A [batch][M][K], B [batch][N][K] -> C = alpha A B^T + beta E1 + diag I
+int tc_gemm_plain(const float* A, const float* Bm, const float* E1, float* C, int M, int N, int K, int batch,
+                  float alpha, float beta, float diag, float* scratch, cudaStream_t st) {
+  const int ldk = (K + 3) & ~3;
+  const size_t na = al4t((size_t)batch * M * ldk), nb = al4t((size_t)batch * N * ldk);
+  float *Ah = scratch, *Al = Ah + na, *Bh = Al + na, *Bl = Bh + nb;
+  if (launch_tcs_split(A, (long long)M * K, batch, M, K, K, ldk, Ah, Al, st)) return 1;
+  if (launch_tcs_split(Bm, (long long)N * K, batch, N, K, K, ldk, Bh, Bl, st)) return 1;
+  TcGemm g;
+  g.A_hi = Ah; g.A_lo = Al; g.B_hi = Bh; g.B_lo = Bl;
+  g.M = M; g.N = N; g.K = K; g.lda = g.ldb = ldk;
+  g.sA = (long long)M * ldk; g.sB = (long long)N * ldk;
+  g.alpha = alpha; g.beta = beta; g.diag = diag;
+  g.E1_hi = E1; g.lde1 = N; g.sE1 = (long long)M * N;
+  g.C_hi = C; g.ldc = N; g.sC = (long long)M * N;
+  return launch_tc_gemm(g, batch, st);
+}
+size_t tc_gemm_plain_scratch_floats(int M, int N, int K, int batch) {
+  const int ldk = (K + 3) & ~3;
+  return 2 * al4t((size_t)batch * M * ldk) + 2 * al4t((size_t)batch * N * ldk);
+}
+
+}  // namespace uglad
