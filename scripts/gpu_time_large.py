@@ -39,7 +39,7 @@ def run(B, D, M, steps=3, force=False):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     print(f"   step {ms:.2f} ms  -> {B*15/ms*1e3:.1f} layer-graphs/s, loss {l.item():.4f}, launches/step {(lib.uglad_launch_count()-c0)//steps}")
-    ops.tune("small_d_max", 232)
+    ops.tune("small_d_max", 166)
 
 run(1, 1000, 10000)
 run(32, 200, 1000)

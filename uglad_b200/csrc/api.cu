@@ -44,7 +44,9 @@ void profile_end(cudaStream_t st) {
 
 // runtime threshold between the eigensolver path and the large-D path (tests lower it to run the
 // large-D kernels on small problems); never above the shared-memory solver's hard limit
-static int g_small_d_max = UGLAD_SMALL_D_MAX;
+// default 166: the largest D whose two-buffer (warm-started) Jacobi solver fits one SM; beyond it
+// the tcgen05 Newton-Schulz chain is faster (measured crossover D ~ 155-180, profiles/r01_path_sweep.log)
+static int g_small_d_max = 166;
 static inline int small_d_max() { return g_small_d_max; }
 
 static inline size_t al4(size_t x) { return (x + 3) & ~(size_t)3; }

@@ -246,7 +246,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const int col = tn * BN + c0 + j;
-            if (col >= p.N) break;
+            if (c0 + j >= BN || col >= p.N) break;   // BN = 112: the last 32-column read overhangs the tile
             float o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) o[e] = alpha * __uint_as_float(v[j + e]);
