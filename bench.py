@@ -15,7 +15,9 @@ Workloads (BASELINE.json configs):
                  gradients per epoch.
   single_d100    configs[1]: one graph, D=100, M=1000 (N=1 only; also reported under "extra"
                  by the default run).
-  consensus_d200 configs[3]: 32 imputations at D=200.
+  consensus_d200 configs[3]: 32 imputations at D=200 (tcgen05 Newton-Schulz path).
+  single_d1000   configs[4]: one graph, D=1000, M=10000 (tcgen05 Newton-Schulz path; reported
+                 under "extra" with its tensor-pipe roofline by the default run).
 Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over
 ranks.  `value` has the covariances resident in HBM; `e2e` starts from the sample matrices in
 pinned host memory every step (H2D copy, covariance, conditioning, fwd+bwd+Adam, loss to
@@ -40,6 +42,7 @@ WORKLOADS = {
     "multitask_d100": dict(B=256, D=100, M=1000, config_index=2),
     "single_d100": dict(B=1, D=100, M=1000, config_index=1),
     "consensus_d200": dict(B=32, D=200, M=1000, config_index=3),
+    "single_d1000": dict(B=1, D=1000, M=10000, config_index=4),
     "demo_d10": dict(B=1, D=10, M=500, config_index=0),
 }
 
@@ -49,7 +52,8 @@ def synth(B, D, M, seed):
     uGLAD_GL.fit does (process_table NORM='min_max')."""
     from uglad_b200.utils import prepare_data
     rng = np.random.default_rng(seed)
-    Xb, _ = prepare_data.get_data(D, [0.05, 0.05], M, batch_size=B, eig_offset=1.0, rng=rng)
+    p = 0.05 if D <= 200 else 0.01
+    Xb, _ = prepare_data.get_data(D, [p, p], M, batch_size=B, eig_offset=1.0, rng=rng)
     Xb = (Xb - Xb.min(1, keepdims=True)) / (Xb.max(1, keepdims=True) - Xb.min(1, keepdims=True))
     return Xb.astype(np.float32)
 
@@ -128,10 +132,13 @@ def cpu_oracle_rate(B, D, M, seed, steps, warmup, max_graphs):
 
 
 def run_reference(args, wl, rank, world):
+    """--impl reference: the reference's CPU path (the oracle port; the reference itself is pure
+    Python/torch and cannot be pip-installed here) on the box's host cores."""
     if rank != 0:
         return
     spec = WORKLOADS[wl]
-    steps, warmup = max(1, min(args.steps, 3)), 1
+    big = spec["D"] >= 500
+    steps, warmup = (1, 0) if big else (max(1, min(args.steps, 3)), 1)
     rate, ms, nb, cores = cpu_oracle_rate(spec["B"], spec["D"], spec["M"], 1234, steps, warmup, max_graphs=32)
     sample = f"{nb} of {spec['B']} graphs per step, {steps} steps after {warmup} warm-up (oracle port, torch CPU, batched)"
     line = {
@@ -148,8 +155,14 @@ def run_reference(args, wl, rank, world):
 
 
 # ------------------------------------------------------------------------------------------
+KERNELS = ((0, "eig_jacobi_small_kernel"), (1, "tc_gemm_kernel"))
+
+
 def time_gpu_workload(name, steps, warmup, rank, world, group, dev, profile=False):
-    """Returns dict(value, ms_per_step, e2e..., launches, eig_ms, eig_launches)."""
+    """One workload on this rank's GPU.  `value`: covariances resident in HBM.  `e2e`: every step
+    starts from the sample matrices in pinned host memory (H2D, covariance, conditioning,
+    fwd + bwd + Adam, loss back to the host).  `prof`: a separate pass with CUDA-event brackets
+    around every launch of the two dominant kernels."""
     import ctypes
     import torch
     import torch.distributed as dist
@@ -197,21 +210,65 @@ def time_gpu_workload(name, steps, warmup, rank, world, group, dev, profile=Fals
 
     for _ in range(warmup):
         step(S)
-    if profile:
-        lib.uglad_profile(1, None, None)
     c0 = lib.uglad_launch_count()
     with ClockSampler(dev.index) as clk:
         ms_total = timed(lambda: step(S), steps)
     launches = lib.uglad_launch_count() - c0
-    eig_ms, eig_n = ctypes.c_double(0), ctypes.c_ulonglong(0)
-    lib.uglad_profile(0, ctypes.byref(eig_ms), ctypes.byref(eig_n))
     for _ in range(min(warmup, 2)):
         e2e_step()
     ms_e2e = timed(e2e_step, steps)
+    prof = None
+    if profile:
+        psteps = max(1, min(steps, 5))
+        lib.uglad_profile(1, None, None)
+        ms_prof = timed(lambda: step(S), psteps)
+        prof = {"steps": psteps, "ms_per_step": ms_prof / psteps}
+        for kind, kname in KERNELS:
+            k_ms, k_n, k_work = ctypes.c_double(0), ctypes.c_ulonglong(0), ctypes.c_double(0)
+            lib.uglad_profile_read(kind, ctypes.byref(k_ms), ctypes.byref(k_n), ctypes.byref(k_work))
+            prof[kname] = {"ms": k_ms.value, "launches": int(k_n.value), "work": k_work.value}
+        lib.uglad_profile(0, None, None)
     units = B * world * L_LAYERS * steps
     return dict(value=units / ms_total * 1e3, ms_per_step=ms_total / steps, e2e_value=units / ms_e2e * 1e3,
                 e2e_ms_per_step=ms_e2e / steps, h2d=int(X_host.numel() * 4), d2h=4, launches=int(launches),
-                eig_ms=eig_ms.value, eig_launches=int(eig_n.value), clocks=clk.summary(), B=B, D=D, M=M)
+                prof=prof, clocks=clk.summary(), B=B, D=D, M=M)
+
+
+def roofline_of(r, peaks):
+    """Roofline object of the workload's dominant kernel (largest share of the profiled step).
+    achieved = algorithmic work of the launches / their CUDA-event durations."""
+    prof = r["prof"]
+    if not prof:
+        return None
+    eig, tcg = prof["eig_jacobi_small_kernel"], prof["tc_gemm_kernel"]
+    step_ms = prof["ms_per_step"] * prof["steps"]
+    if tcg["launches"] and tcg["ms"] >= eig["ms"]:
+        key = "bf16_tflops_sustained"
+        peak = peaks.get(key)
+        src = f"measured (MEASURED_PEAKS.json {key}: cuBLAS dense bf16 inside a long step)"
+        if not peak:
+            peak, src = 1400.0, "fallback (B200_PROFILING.md sustained bf16)"
+        achieved = tcg["work"] / (tcg["ms"] * 1e-3) / 1e12
+        return {"bound": "tensor", "kernel": "tc_gemm_kernel (tcgen05.mma kind::tf32, 3xTF32 split operands)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": src, "avg_launch_ms": tcg["ms"] / tcg["launches"],
+                "launches_per_step": tcg["launches"] / prof["steps"], "kernel_share_of_step": tcg["ms"] / step_ms,
+                "tf32_pipe_frac": 3.0 * achieved / (peak / 2.0),
+                "note": "achieved counts the algorithmic 2MNK flops per product; every product issues three "
+                        "TF32 MMAs and the TF32 pipe peaks at half the bf16 rate, so the tensor pipe itself "
+                        "runs at tf32_pipe_frac of its own peak"}
+    peak = peaks.get("hbm_gbs")
+    src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    if not peak:
+        peak, src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = eig["work"] / (eig["ms"] * 1e-3) / 1e9 if eig["launches"] else None
+    return {"bound": "hbm", "kernel": "eig_jacobi_small_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": src,
+            "avg_launch_ms": (eig["ms"] / eig["launches"]) if eig["launches"] else None,
+            "launches_per_step": eig["launches"] / prof["steps"],
+            "kernel_share_of_step": eig["ms"] / step_ms,
+            "note": "shared-memory-resident Jacobi solver: the binding limit is SM issue/smem latency, not HBM "
+                    "(see DESIGN.md)"}
 
 
 def main():
@@ -221,7 +278,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="multitask_d100", choices=sorted(WORKLOADS))
-    ap.add_argument("--no-extra", action="store_true", help="skip the extra single-graph measurement")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra per-config measurements")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -243,32 +300,29 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
 
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+
     wl = args.workload
     r = time_gpu_workload(wl, args.steps, args.warmup, rank, world, group, dev, profile=True)
     spec = WORKLOADS[wl]
     extra = {}
     if world == 1 and not args.no_extra and wl == "multitask_d100":
-        x = time_gpu_workload("single_d100", args.steps, args.warmup, rank, world, group, dev)
-        extra["single_d100"] = {"baseline_config_index": 1, "value": x["value"], "unit": "layer-graphs/s",
-                                "ms_per_step": x["ms_per_step"], "e2e_value": x["e2e_value"]}
+        for name, st, wu in (("single_d100", args.steps, args.warmup), ("consensus_d200", min(args.steps, 10), 3),
+                             ("single_d1000", min(args.steps, 5), 3)):
+            x = time_gpu_workload(name, st, wu, rank, world, group, dev, profile=True)
+            extra[name] = {"baseline_config_index": WORKLOADS[name]["config_index"], "value": x["value"],
+                           "unit": "layer-graphs/s", "ms_per_step": x["ms_per_step"], "e2e_value": x["e2e_value"],
+                           "gpu_launches": x["launches"], "roofline": roofline_of(x, peaks)}
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json hbm_gbs)") if peaks.get("hbm_gbs") \
-            else (6650.0, "fallback (B200_PROFILING.md)")
-        # dominant kernel: eig_jacobi_small_kernel.  Algorithmic HBM bytes per layer-graph:
-        # read S, theta_prev and the warm-start eigenvectors (3 D^2 floats), write the
-        # eigenvectors (D^2) and 3 D-vectors.  ("Roofline")
         D, B = r["D"], r["B"]
-        bytes_per_launch = B * (4 * D * D + 3 * D) * 4
-        achieved = None
-        if r["eig_launches"]:
-            achieved = bytes_per_launch / (r["eig_ms"] / r["eig_launches"] * 1e-3) / 1e9
-        cpu_rate, cpu_ms, cpu_nb, cores = cpu_oracle_rate(spec["B"], spec["D"], spec["M"], 1234, 2, 1, max_graphs=32)
+        big = D >= 500
+        cpu_rate, cpu_ms, cpu_nb, cores = cpu_oracle_rate(spec["B"], spec["D"], spec["M"], 1234, 1 if big else 2,
+                                                          0 if big else 1, max_graphs=32)
         line = {
             "metric": "unrolled-layer-graphs/sec fwd+bwd", "value": r["value"], "unit": "layer-graphs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
@@ -276,19 +330,14 @@ def main():
             "config": {"workload": wl, "baseline_config_index": spec["config_index"], "graphs_per_gpu": B,
                        "graphs_total": B * world, "D": D, "M": r["M"], "L": L_LAYERS, "H": 3,
                        "parallelism": f"graph-sharded x{world}", "l2_policy": "working set per step exceeds L2 "
-                       "(saved eigenvectors/theta of 15 layers: %.0f MB)" % (B * D * D * 4 * 3 * L_LAYERS / 1e6)},
+                       "(saved theta / theta_k1 / eigenvectors of 15 layers: %.0f MB)" % (B * D * D * 4 * 3 * L_LAYERS / 1e6)},
             "clocks": r["clocks"],
             "e2e": {"value": r["e2e_value"], "unit": "layer-graphs/s", "ms_per_step": r["e2e_ms_per_step"],
                     "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
             "gpu_launches": r["launches"],
-            "roofline": {"bound": "hbm", "kernel": "eig_jacobi_small_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
-                         "peak_source": peak_src, "avg_launch_ms": (r["eig_ms"] / r["eig_launches"]) if r["eig_launches"] else None,
-                         "kernel_share_of_step": (r["eig_ms"] / (r["ms_per_step"] * args.steps)) if r["eig_launches"] else None,
-                         "note": "shared-memory-resident Jacobi solver: the binding limit is SM issue/smem "
-                                 "latency, not HBM (see DESIGN.md)"},
+            "roofline": roofline_of(r, peaks),
             "cpu_baseline": {"value": cpu_rate, "unit": "layer-graphs/s", "cores": cores, "kind": "port",
-                             "sample": f"{cpu_nb} of {spec['B']} graphs per step, 2 steps after 1 warm-up (oracle port, torch CPU)"},
+                             "sample": f"{cpu_nb} of {spec['B']} graphs per step (oracle port, torch CPU)"},
             "extra": extra,
         }
         print(json.dumps(line), flush=True)

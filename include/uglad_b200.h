@@ -115,6 +115,10 @@ int uglad_glasso_loss(const float* theta, const float* S, int B, int D, int S_ba
  * event brackets on or off.                                                               */
 unsigned long long uglad_launch_count(void);
 int uglad_profile(int enable, double* total_ms, unsigned long long* launches);
+/* read (without clearing) what has accumulated since the last uglad_profile call for one kernel
+ * class: kind 0 = Jacobi eigensolver (work = algorithmic HBM bytes), kind 1 = tcgen05 3xTF32 GEMM
+ * (work = algorithmic flops 2 M N K batch).                                                  */
+int uglad_profile_read(int kind, double* total_ms, unsigned long long* launches, double* work);
 
 /* developer knobs used by the tuning scripts and tests: "eig_lp" (lanes per column pair, 0 = auto),
  * "eig_keepg" (-1 auto / 0 / 1: keep A + sigma I in a second shared-memory buffer),

@@ -281,7 +281,7 @@ def spectral_forward_backward(S, P, L=15, init_diag=0, lambda_init=1.0, exact_sq
         dS = np.einsum("bii->bi", S)
         theta = np.stack([np.diag(1.0 / (dS[b] + t0)) for b in range(B)])
     else:
-        theta = np.einsum("bik,bk,bjk->bij", VS, 1.0 / (sS + t0), VS)
+        theta = np.matmul(VS * (1.0 / (sS + t0))[:, None, :], VS.transpose(0, 2, 1))
     theta0 = theta
     lam_in, lam_h, lam = _mlp_lambda_np(W, lambda_init, 0.0)
     saved, lam_feats = [], [(lam_in, lam_h, lam)]
@@ -290,7 +290,7 @@ def spectral_forward_backward(S, P, L=15, init_diag=0, lambda_init=1.0, exact_sq
         beta, V = np.linalg.eigh(b)
         mu = beta * beta + 4.0 / lam
         s = np.sqrt(mu) if exact_sqrt else np.stack([ns_scalar_forward(m) for m in mu])
-        x = np.einsum("bik,bk,bjk->bij", V, 0.5 * (s - beta), V)
+        x = np.matmul(V * (0.5 * (s - beta))[:, None, :], V.transpose(0, 2, 1))
         feats, h1, h2, rho = _mlp_rho_np(W, x, S, theta)
         z = np.sign(x) * np.maximum(np.abs(x) - rho, 0.0)
         normF = float(np.mean(np.sum((z - x) ** 2, axis=(1, 2))))
@@ -305,7 +305,7 @@ def spectral_forward_backward(S, P, L=15, init_diag=0, lambda_init=1.0, exact_sq
     loss = float(np.sum(-logdet + np.einsum("bij,bji->b", LS, theta)) / B)
     # backward
     g = {k: np.zeros_like(v) for k, v in W.items()}
-    G = (-np.einsum("bik,bk,bjk->bij", Vt, 1.0 / ev, Vt) + LS.transpose(0, 2, 1)) / B
+    G = (-np.matmul(Vt * (1.0 / ev)[:, None, :], Vt.transpose(0, 2, 1)) + LS.transpose(0, 2, 1)) / B
     g_lams = np.zeros(L)
     for k in reversed(range(L)):
         lam_k, beta, V, s, x, feats, h1, h2, rho = saved[k]
@@ -328,7 +328,7 @@ def spectral_forward_backward(S, P, L=15, init_diag=0, lambda_init=1.0, exact_sq
         # spectral backward of x = V f(beta) V^T; only the symmetric part of the incoming
         # gradient can reach a parameter, so it is symmetrised here.
         g_x = 0.5 * (g_x + g_x.transpose(0, 2, 1))
-        Gt = np.einsum("bki,bkl,blj->bij", V, g_x, V)
+        Gt = np.matmul(np.matmul(V.transpose(0, 2, 1), g_x), V)
         g_b = np.empty_like(Gt)
         for bb in range(B):
             if exact_sqrt:
@@ -339,7 +339,7 @@ def spectral_forward_backward(S, P, L=15, init_diag=0, lambda_init=1.0, exact_sq
             H = C * Gt[bb]
             g_lams[k] += -4.0 / lam_k ** 2 * np.trace(H)
             g_b[bb] = 0.5 * (beta[bb][:, None] + beta[bb][None, :]) * (2.0 * H) - 0.5 * Gt[bb]
-        g_b = np.einsum("bik,bkl,bjl->bij", V, g_b, V)
+        g_b = np.matmul(np.matmul(V, g_b), V.transpose(0, 2, 1))
         g_lams[k] += -np.sum(S * g_b) / lam_k ** 2
         G = g_prev - g_b
     # theta_init
@@ -348,7 +348,7 @@ def spectral_forward_backward(S, P, L=15, init_diag=0, lambda_init=1.0, exact_sq
         g["theta_init_offset"] += -np.sum(np.einsum("bii->bi", G) / (dS + t0) ** 2)
     else:
         Gs = 0.5 * (G + G.transpose(0, 2, 1))
-        Gt = np.einsum("bki,bkl,bli->bi", VS, Gs, VS)
+        Gt = np.einsum("bki,bki->bi", VS, np.matmul(Gs, VS))
         g["theta_init_offset"] += -np.sum(Gt / (sS + t0) ** 2)
     # lambda MLP backward (inputs are constants)
     for k in range(L):

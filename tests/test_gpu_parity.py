@@ -385,3 +385,31 @@ def test_large_path_covariance_repair(dev, force_large_path, M, D):
     X = rng.standard_normal((2, M, D))
     S = prepare_data.get_covariance(X, offset=0.1).cpu().numpy()
     assert rel(S, O.covariance(X, offset=0.1)) < 2e-5
+
+
+LARGE = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "large", "*.npz")))
+
+
+@pytest.mark.parametrize("path", LARGE, ids=[os.path.basename(p)[:-4] for p in LARGE])
+def test_d1000_against_reference_golden(dev, path):
+    """BASELINE configs[4] (D=1000, L=15) against the real reference run on the CPU
+    (tests/golden/make_golden.py large): theta on every 8th row, its Frobenius norm and support
+    size, the loss and the 42 gradients."""
+    from uglad_b200 import main as ug, ops
+    ops.reset_warm_start()
+    g = np.load(path)
+    D, L, step = int(g["D"]), int(g["L"]), int(g["row_step"])
+    S = np.zeros((D, D), np.float32)
+    S[np.triu_indices(D)] = g["S_triu"]
+    S = S + np.triu(S, 1).T
+    model = load_model(g, "p0")
+    theta, loss = ug.forward_uGLAD(torch.tensor(S[None], device=dev), model, L=L, INIT_DIAG=0)
+    loss.backward()
+    th = theta.detach().cpu().numpy()[0]
+    assert rel(th[::step], g["theta0_rows"]) < THETA_TOL
+    assert edge_sets_match(th[::step], g["theta0_rows"])
+    assert abs(np.linalg.norm(th.astype(np.float64)) - float(g["theta0_fro"])) < THETA_TOL * float(g["theta0_fro"])
+    assert abs(int((th != 0).sum()) - int(g["theta0_nnz"])) <= 2e-4 * int(g["theta0_nnz"]) + 2
+    assert abs(loss.item() - float(g["loss0"])) < 1e-4 * max(1.0, abs(float(g["loss0"])))
+    for k, p in model.named_parameters():
+        assert rel(p.grad.cpu().numpy(), g["g0/" + k]) < 1e-3, k

@@ -23,23 +23,28 @@ void set_error(const char* fmt, ...) {
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-// CUDA-event brackets around the dominant kernel, switched on by uglad_profile(1)
+// CUDA-event brackets around the two dominant kernels, switched on by uglad_profile(1):
+// kind 0 = Jacobi eigensolver, kind 1 = tcgen05 3xTF32 GEMM.  `work` is the launch's algorithmic
+// work (bytes for kind 0, flops for kind 1).
+struct ProfEvent { cudaEvent_t a, b; int kind; double work; };
 static std::mutex g_prof_mu;
 static bool g_prof_on = false;
-static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
-void profile_begin(cudaStream_t st) {
+static std::vector<ProfEvent> g_prof_events;
+void profile_begin(cudaStream_t st, int kind, double work) {
   if (!g_prof_on) return;
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  cudaEvent_t a, b;
-  cudaEventCreate(&a);
-  cudaEventCreate(&b);
-  cudaEventRecord(a, st);
-  g_prof_events.emplace_back(a, b);
+  ProfEvent e;
+  cudaEventCreate(&e.a);
+  cudaEventCreate(&e.b);
+  e.kind = kind;
+  e.work = work;
+  cudaEventRecord(e.a, st);
+  g_prof_events.push_back(e);
 }
 void profile_end(cudaStream_t st) {
   if (!g_prof_on) return;
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  if (!g_prof_events.empty()) cudaEventRecord(g_prof_events.back().second, st);
+  if (!g_prof_events.empty()) cudaEventRecord(g_prof_events.back().b, st);
 }
 
 // runtime threshold between the eigensolver path and the large-D path (tests lower it to run the
@@ -435,22 +440,33 @@ int uglad_glasso_loss(const float* theta, const float* S, int B, int D, int S_ba
 
 unsigned long long uglad_launch_count(void) { return g_launches.load(); }
 
-int uglad_profile(int enable, double* total_ms, unsigned long long* launches) {
+int uglad_profile_read(int kind, double* total_ms, unsigned long long* launches, double* work) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  double tot = 0.0;
+  double tot = 0.0, wk = 0.0;
   unsigned long long n = 0;
   for (auto& e : g_prof_events) {
+    if (e.kind != kind) continue;
     float ms = 0.f;
-    if (cudaEventSynchronize(e.second) == cudaSuccess && cudaEventElapsedTime(&ms, e.first, e.second) == cudaSuccess) {
+    if (cudaEventSynchronize(e.b) == cudaSuccess && cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) {
       tot += ms;
+      wk += e.work;
       ++n;
     }
-    cudaEventDestroy(e.first);
-    cudaEventDestroy(e.second);
   }
-  g_prof_events.clear();
   if (total_ms) *total_ms = tot;
   if (launches) *launches = n;
+  if (work) *work = wk;
+  return 0;
+}
+
+int uglad_profile(int enable, double* total_ms, unsigned long long* launches) {
+  uglad_profile_read(0, total_ms, launches, nullptr);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& e : g_prof_events) {
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
+  g_prof_events.clear();
   g_prof_on = enable != 0;
   return 0;
 }

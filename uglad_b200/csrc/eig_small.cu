@@ -450,7 +450,7 @@ static int launch_cfg(const EigArgs& a, int B, size_t smem, cudaStream_t st) {
   if (threads < a.D) threads = ((a.D + 31) / 32) * 32;  // the power iteration wants a thread per row
   UGLAD_CUDA(cudaFuncSetAttribute(eig_jacobi_small_kernel<LP, CH>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  profile_begin(st);
+  profile_begin(st, 0, (double)B * (4.0 * a.D * a.D + 3.0 * a.D) * 4.0);
   eig_jacobi_small_kernel<LP, CH><<<B, threads, smem, st>>>(a);
   profile_end(st);
   UGLAD_CHECK_LAUNCH("eig_jacobi_small_kernel");

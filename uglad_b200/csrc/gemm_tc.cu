@@ -419,7 +419,9 @@ static int launch_tc(const TcGemm& g, int batch, cudaStream_t st) {
     UGLAD_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = (int)(total < g_num_sms ? total : g_num_sms);
+  profile_begin(st, 1, 2.0 * g.M * g.N * g.K * batch);
   tc_gemm_kernel<BN><<<grid, tc::THREADS, C::SMEM, st>>>(mAh, mAl, mBh, mBl, p);
+  profile_end(st);
   UGLAD_CHECK_LAUNCH("tc_gemm_kernel");
   return 0;
 }

@@ -32,7 +32,7 @@ int launch_eig_small(const EigArgs& a, int B, cudaStream_t st);
 int eig_small_tune(const char* key, int value);
 int launch_eig(const EigArgs& a, int B, cudaStream_t st);  // dispatch on D
 // optional CUDA-event bracket around the eigensolver launches (bench.py's roofline leg)
-void profile_begin(cudaStream_t st);
+void profile_begin(cudaStream_t st, int kind, double work);  // kind 0 eigensolver (bytes), 1 tcgen05 GEMM (flops)
 void profile_end(cudaStream_t st);
 size_t eig_scratch_floats(int B, int D);
 

@@ -35,13 +35,7 @@ def loss_uGLAD(theta: torch.Tensor, S: torch.Tensor, struct_theta: Optional[torc
     """main.py:289-335: sum_b(-logdet theta_b + <S_b, theta_b>) / B with B = S.shape[0]
     (the number of graphs over all processes when `group` shards them), plus the optional
     log-cosh structure prior."""
-    B = S.shape[0]
-    if group is not None:
-        import torch.distributed as dist
-        if dist.get_world_size(group) > 1:
-            cnt = torch.tensor([B], device=S.device, dtype=torch.int64)
-            dist.all_reduce(cnt, group=group)
-            B = int(cnt.item())
+    B = ops.global_graph_count(S.shape[0], S.device, group)
     loss = ops.GlassoLossFunction.apply(theta, S, float(B))
     if struct_theta is not None:
         D = S.shape[-1]

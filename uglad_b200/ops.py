@@ -120,6 +120,41 @@ def tune(key: str, value: int):
     check(_lib.load().uglad_tune(key.encode(), int(value)), "uglad_tune")
 
 
+# ---- graph-sharded execution (one process per GPU) ------------------------------------------------
+# The graphs of a multitask / consensus batch are independent except for two scalars per epoch
+# path: the batch MEAN of ||Z - X||_F^2 that feeds lambda_f after every layer (glad.py:147) and the
+# 1/B of the loss (main.py:315).  These helpers are the whole distributed protocol; they are
+# backend-agnostic (NCCL on the GPUs, gloo in the CPU tests).
+def global_graph_count(B: int, device, group) -> int:
+    """Number of graphs over all ranks of `group` (B when not distributed)."""
+    if group is None:
+        return B
+    import torch.distributed as dist
+    if dist.get_world_size(group) == 1:
+        return B
+    cnt = torch.tensor([B], device=device, dtype=torch.int64)
+    dist.all_reduce(cnt, group=group)
+    return int(cnt.item())
+
+
+def run_sharded_layers(L: int, layer_fn, normf: torch.Tensor, group) -> None:
+    """Drive the L unrolled layers of this rank's shard: layer_fn(k) leaves the LOCAL sum of
+    ||Z - X||_F^2 in normf[k]; it is all-reduced before layer k+1 turns it into lambda_{k+1}."""
+    import torch.distributed as dist
+    for k in range(L):
+        layer_fn(k)
+        if k + 1 < L:
+            dist.all_reduce(normf[k:k + 1], group=group)
+
+
+def allreduce_shared_gradients(gp: torch.Tensor, group) -> torch.Tensor:
+    """The one collective of the data path: the packed rho_l1 / lambda_f / theta_init_offset
+    gradient (42 floats for H=3) summed over the shards."""
+    import torch.distributed as dist
+    dist.all_reduce(gp, group=group)
+    return gp
+
+
 class GladFunction(torch.autograd.Function):
     """theta_pred = glad(S; params)  (glad.py:74-150) with the hand-written backward."""
 
@@ -130,14 +165,10 @@ class GladFunction(torch.autograd.Function):
         flat_params = _f32c(flat_params, "params")
         B, D, _ = S.shape
         world = 1
-        B_total = B
         if group is not None:
             import torch.distributed as dist
             world = dist.get_world_size(group)
-            if world > 1:
-                cnt = torch.tensor([B], device=S.device, dtype=torch.int64)
-                dist.all_reduce(cnt, group=group)
-                B_total = int(cnt.item())
+        B_total = global_graph_count(B, S.device, group)
         dims = make_dims(B, D, L, H, init_diag, B_total, exact_sqrt, lambda_init)
         if flat_params.numel() != lib.uglad_param_count(H):
             raise _lib.UgladError("packed parameter vector has the wrong length")
@@ -156,16 +187,15 @@ class GladFunction(torch.autograd.Function):
             check(lib.uglad_glad_forward(C.byref(dims), _ptr(S), _ptr(flat_params), _ptr(wS), _ptr(VtS),
                                          _ptr(ws), _ptr(warm), st), "uglad_glad_forward")
         else:
-            import torch.distributed as dist
             check(lib.uglad_glad_init_forward(C.byref(dims), _ptr(S), _ptr(flat_params), _ptr(wS), _ptr(VtS),
                                               _ptr(ws), st), "uglad_glad_init_forward")
             off = lib.uglad_workspace_offset(C.byref(dims), b"normf")
-            normf = ws[off:off + L]
-            for k in range(L):
+
+            def layer(k):
                 check(lib.uglad_glad_layer_forward(C.byref(dims), k, _ptr(S), _ptr(flat_params), _ptr(ws),
                                                    _ptr(warm), st), "uglad_glad_layer_forward")
-                if k + 1 < L:  # the mean of glad.py:147 runs over every process's graphs
-                    dist.all_reduce(normf[k:k + 1], group=group)
+
+            run_sharded_layers(L, layer, ws[off:off + L], group)
         if warm_start_enabled:
             _warm.clear()  # keep exactly one earlier workspace alive
             _warm[wkey] = ws
@@ -183,9 +213,8 @@ class GladFunction(torch.autograd.Function):
         wS, VtS = (ctx.eig.wS, ctx.eig.VtS) if ctx.eig is not None else (None, None)
         check(lib.uglad_glad_backward(C.byref(dims), _ptr(ctx.S), _ptr(ctx.params), _ptr(wS), _ptr(VtS),
                                       _ptr(ctx.ws), _ptr(g), _ptr(gp), _stream(g)), "uglad_glad_backward")
-        if ctx.world > 1:  # the one collective of the data path: shared MLP gradients
-            import torch.distributed as dist
-            dist.all_reduce(gp, group=ctx.group)
+        if ctx.world > 1:
+            allreduce_shared_gradients(gp, ctx.group)
         return None, gp, None, None, None, None, None, None
 
 
