@@ -164,6 +164,25 @@ def test_training_loop_against_reference_golden(dev, path):
         assert rel(c, g["consensus"]) < THETA_TOL
 
 
+def test_eigensolver_path_with_simt_products(dev):
+    """The FP32 SIMT products behind the "use_tc" = 0 knob give the same answer as the tcgen05 ones."""
+    from uglad_b200 import main as ug, ops
+    g = np.load(os.path.join(ROOT, "tests", "golden", "d100_lowrho.npz"))
+    S = torch.tensor(g["S"], device=dev)
+    ops.tune("use_tc", 0)
+    try:
+        ops.reset_warm_start()
+        model = load_model(g, "p0")
+        theta, loss = ug.forward_uGLAD(S, model, L=int(g["L"]), INIT_DIAG=int(g["init_diag"]))
+        loss.backward()
+        assert rel(theta.detach().cpu().numpy(), g["theta0"]) < THETA_TOL
+        for k, p in model.named_parameters():
+            assert rel(p.grad.cpu().numpy(), g["g0/" + k]) < 1e-3, k
+    finally:
+        ops.tune("use_tc", 1)
+        ops.reset_warm_start()
+
+
 def test_warm_start_does_not_change_the_result(dev):
     from uglad_b200 import main as ug, ops
     g = np.load(CASES[0])

@@ -59,8 +59,9 @@ static inline size_t al4(size_t x) { return (x + 3) & ~(size_t)3; }
 struct Ws {
   size_t theta, X, Vt, beta, sroot, f, snorm, lam, lamfeat, normf, info, part, counter, f0;
   size_t T1, T2, G0, G1, GF3, rho_part, trh_part, sgb_part, t0_part, eig_scratch, ns_scratch, chol_scratch, total;
-  size_t n1, n2, nblk;
-  int NPR;
+  size_t VtS, VS, sp;   // eigensolver path: split (hi, lo) eigenvectors per layer + 5 split scratch matrices
+  size_t n1, n2, n2p, nblk;
+  int NPR, ldp;
   bool large;   // D > small_d_max(): Newton-Schulz GEMM path, no eigenvectors are stored
 };
 static Ws ws_layout(const uglad_dims* d) {
@@ -76,6 +77,11 @@ static Ws ws_layout(const uglad_dims* d) {
   w.theta = take((L + 1) * w.n2);
   w.X = take(L * w.n2);
   w.Vt = take(w.large ? 0 : L * w.n2);
+  w.ldp = (d->D + 3) & ~3;
+  w.n2p = al4(B * D * (size_t)w.ldp);
+  w.VtS = take(w.large ? 0 : L * 2 * w.n2p);
+  w.VS = take(w.large ? 0 : L * 2 * w.n2p);
+  w.sp = take(w.large ? 0 : 10 * w.n2p);
   w.beta = take(L * w.n1);
   w.sroot = take(L * w.n1);
   w.f = take(L * w.n1);
@@ -127,6 +133,19 @@ static int spectral_recon(const float* Vt, const float* f, float* C, int B, int 
   g.kscale = f; g.sK = D;
   g.alpha = alpha; g.beta = alpha; g.E1 = E1; g.sE1 = sE1; g.lde1 = D;
   return launch_gemm(g, B, st);
+}
+// tcgen05 3xTF32 product of two split [B][D][ldp] matrices: C = A B^T (split or plain output)
+static int tc_mm(const float* Ah, const float* Al, const float* Bh, const float* Bl, float* Ch, float* Cl,
+                 int B, int D, int ldp, cudaStream_t st) {
+  TcGemm g;
+  g.A_hi = Ah; g.A_lo = Al; g.B_hi = Bh; g.B_lo = Bl;
+  g.M = g.N = g.K = D;
+  g.lda = g.ldb = ldp;
+  g.sA = g.sB = (long long)D * ldp;
+  g.C_hi = Ch; g.C_lo = Cl;
+  g.ldc = Cl ? ldp : D;
+  g.sC = Cl ? (long long)D * ldp : (long long)D * D;
+  return launch_tc_gemm(g, B, st);
 }
 static int bgemm(const float* A, int tA, const float* Bm, int tB, float* C, int B, int D, cudaStream_t st) {
   GemmArgs g;
@@ -322,7 +341,15 @@ int uglad_glad_layer_forward(const uglad_dims* d, int k, const float* S, const f
   a.warmVt = warm_ws ? warm_ws + w.Vt + (size_t)k * w.n2 : nullptr;
   a.D = D; a.shift_mode = 1; a.tail = TAIL_LAYER; a.exact_sqrt = d->exact_sqrt;
   if (launch_eig(a, B, st)) return 1;
-  if (spectral_recon(Vk, fk, Xk, B, D, 1.f, nullptr, 0, st)) return 1;
+  if (ns_use_tc()) {  // X = (V diag f) V^T on the tensor pipe; the split eigenvectors are kept for the backward
+    float* VtSk = ws + w.VtS + (size_t)k * 2 * w.n2p;
+    float* VSk = ws + w.VS + (size_t)k * 2 * w.n2p;
+    float* VF = ws + w.sp;
+    if (launch_eigvec_split(Vk, fk, B, D, w.ldp, VtSk, VtSk + w.n2p, VSk, VSk + w.n2p, VF, VF + w.n2p, st)) return 1;
+    if (tc_mm(VF, VF + w.n2p, VSk, VSk + w.n2p, Xk, nullptr, B, D, w.ldp, st)) return 1;
+  } else if (spectral_recon(Vk, fk, Xk, B, D, 1.f, nullptr, 0, st)) {
+    return 1;
+  }
   return launch_z_update_fwd(Xk, S, theta_prev, params, d->H, B, D, theta_next, ws + w.part,
                              ws + w.normf + k, reinterpret_cast<unsigned*>(ws + w.counter), st);
 }
@@ -356,6 +383,29 @@ int uglad_glad_backward(const uglad_dims* d, const float* S, const float* params
     const float* theta_prev = ws + w.theta + (size_t)k * w.n2;
     const float* Xk = ws + w.X + (size_t)k * w.n2;
     const float* Vk = ws + w.Vt + (size_t)k * w.n2;
+    if (!w.large && ns_use_tc()) {
+      // eigenbasis round trip on the tensor pipe (every right operand is K-major as stored):
+      //   U1 = Vt GX, Gt = U1 Vt^T, W = Phi o Gt, P = V W, Gb = P V^T
+      const float* VtSk = ws + w.VtS + (size_t)k * 2 * w.n2p;
+      const float* VSk = ws + w.VS + (size_t)k * 2 * w.n2p;
+      float* GXs = ws + w.sp + 2 * w.n2p;
+      float* U1 = ws + w.sp + 4 * w.n2p;
+      float* Gt = ws + w.sp + 6 * w.n2p;
+      float* Pm = ws + w.sp + 8 * w.n2p;
+      if (launch_z_update_bwd(G, Xk, S, theta_prev, params, d->H, B, D, GXs, GF3,
+                              ws + w.rho_part + (size_t)k * w.nblk * w.NPR, st, GXs + w.n2p, w.ldp)) return 1;
+      if (tc_mm(VtSk, VtSk + w.n2p, GXs, GXs + w.n2p, U1, U1 + w.n2p, B, D, w.ldp, st)) return 1;
+      if (tc_mm(U1, U1 + w.n2p, VtSk, VtSk + w.n2p, Gt, Gt + w.n2p, B, D, w.ldp, st)) return 1;
+      if (launch_phi_split(Gt, Gt + w.n2p, ws + w.beta + (size_t)k * w.n1, ws + w.sroot + (size_t)k * w.n1,
+                           ws + w.snorm + (size_t)k * B, d->exact_sqrt, B, D, w.ldp,
+                           ws + w.trh_part + (size_t)k * w.nblk, st)) return 1;
+      if (tc_mm(VSk, VSk + w.n2p, Gt, Gt + w.n2p, Pm, Pm + w.n2p, B, D, w.ldp, st)) return 1;
+      if (tc_mm(Pm, Pm + w.n2p, VSk, VSk + w.n2p, T1, nullptr, B, D, w.ldp, st)) return 1;
+      float* Gn = Gbuf[k & 1];
+      if (launch_gb_finish(T1, GF3, S, B, D, Gn, ws + w.sgb_part + (size_t)k * w.nblk, st)) return 1;
+      G = Gn;
+      continue;
+    }
     if (launch_z_update_bwd(G, Xk, S, theta_prev, params, d->H, B, D, T1, GF3,
                             ws + w.rho_part + (size_t)k * w.nblk * w.NPR, st)) return 1;
     if (w.large) {
@@ -392,8 +442,9 @@ int uglad_glad_backward(const uglad_dims* d, const float* S, const float* params
 
 size_t uglad_loss_scratch_floats(int B, int D) {
   const size_t n2 = (size_t)B * D * D, n1 = (size_t)B * D;
-  if (D > small_d_max()) return 2 * al4(n2) + 2 * al4(B) + 8 + al4(chol_scratch_floats(B, D));
-  return al4(n2) + 2 * al4(n1) + 2 * al4(B) + al4(4 * (size_t)B) + 8 + al4(eig_scratch_floats(B, D));
+  const size_t lp = al4((size_t)B * loss_blocks_per_graph(D));
+  if (D > small_d_max()) return 2 * al4(n2) + 2 * al4(B) + 8 + lp + al4(chol_scratch_floats(B, D));
+  return al4(n2) + 2 * al4(n1) + 2 * al4(B) + al4(4 * (size_t)B) + 8 + lp + al4(eig_scratch_floats(B, D));
 }
 
 int uglad_glasso_loss(const float* theta, const float* S, int B, int D, int S_batch, float Bdiv,
@@ -409,11 +460,12 @@ int uglad_glasso_loss(const float* theta, const float* S, int B, int D, int S_ba
     float* logdet = W + al4(n2);
     float* lossb = logdet + al4(B);
     float* counter = lossb + al4(B);
-    float* cs = counter + 8;
+    float* lpart = counter + 8;
+    float* cs = lpart + al4((size_t)B * loss_blocks_per_graph(D));
     UGLAD_CUDA(cudaMemsetAsync(counter, 0, 4 * sizeof(float), st));
     if (launch_copy_shift(theta, (long long)D * D, B, D, 0.f, nullptr, Lf, st)) return 1;
     if (chol_factor(Lf, B, D, 0.f, nullptr, logdet, cs, st)) return 1;
-    if (launch_loss_terms(theta, S, sSl, logdet, B, D, Bdiv, lossb, loss_out,
+    if (launch_loss_terms(theta, S, sSl, logdet, B, D, Bdiv, lpart, lossb, loss_out,
                           reinterpret_cast<unsigned*>(counter), st)) return 1;
     if (grad_theta) return chol_inverse(Lf, B, D, W, grad_theta, -1.0f / Bdiv, S, sSl, 1.0f / Bdiv, cs, st);
     return 0;
@@ -425,14 +477,15 @@ int uglad_glasso_loss(const float* theta, const float* S, int B, int D, int S_ba
   float* lossb = logdet + al4(B);
   float* info = lossb + al4(B);
   float* counter = info + al4(4 * (size_t)B);
-  float* escr = counter + 8;
+  float* lpart = counter + 8;
+  float* escr = lpart + al4((size_t)B * loss_blocks_per_graph(D));
   UGLAD_CUDA(cudaMemsetAsync(counter, 0, 4 * sizeof(float), st));
   EigArgs a;
   a.A = theta; a.w = w; a.Vt = Vt; a.info = info; a.f = f; a.snorm = logdet; a.scratch = escr;
   a.D = D; a.shift_mode = 0; a.tail = TAIL_LOSS;
   if (launch_eig(a, B, st)) return 1;
   const long long sS = (S_batch == 1) ? 0 : (long long)D * D;
-  if (launch_loss_terms(theta, S, sS, logdet, B, D, Bdiv, lossb, loss_out,
+  if (launch_loss_terms(theta, S, sS, logdet, B, D, Bdiv, lpart, lossb, loss_out,
                         reinterpret_cast<unsigned*>(counter), st)) return 1;
   if (grad_theta) return spectral_recon(Vt, f, grad_theta, B, D, 1.0f / Bdiv, S, sS, st);
   return 0;

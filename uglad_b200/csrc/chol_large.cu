@@ -20,6 +20,8 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(float* A, int D, int j0,
                                                         int* fail) {
   __shared__ float Ls[CB][CBP];
   __shared__ float Ws[CB][CBP];
+  __shared__ float piv_s[CB];
+  __shared__ double redd[32];
   __shared__ int s_fail;
   const int b = blockIdx.x, tid = threadIdx.x;
   float* Ab = A + (size_t)b * D * D;
@@ -36,7 +38,8 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(float* A, int D, int j0,
     Ws[i][j] = 0.f;
   }
   __syncthreads();
-  double ld = 0.0;
+  if (tid < CB) piv_s[tid] = 1.f;
+  const int tx = tid & 15, ty = tid >> 4;   // 16 x 16 threads over the trailing triangle
   for (int j = 0; j < nb; ++j) {
     const float piv = Ls[j][j];
     __syncthreads();
@@ -45,20 +48,21 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(float* A, int D, int j0,
       break;  // uniform: every thread read the same pivot
     }
     const float r = sqrtf(piv), ir = 1.f / r;
-    if (tid == 0) ld += log((double)r);
+    if (tid == 0) piv_s[j] = r;
     // scale column j
     for (int i = j + tid; i < nb; i += 256) Ls[i][j] = (i == j) ? r : Ls[i][j] * ir;
     __syncthreads();
     // rank-1 update of the trailing lower triangle
-    const int m = nb - j - 1;
-    for (int idx = tid; idx < m * m; idx += 256) {
-      const int i = j + 1 + idx / m, k = j + 1 + idx % m;
-      if (k <= i) Ls[i][k] = fmaf(-Ls[i][j], Ls[k][j], Ls[i][k]);
+    for (int i = j + 1 + ty; i < nb; i += 16) {
+      const float lij = Ls[i][j];
+      for (int k = j + 1 + tx; k <= i; k += 16) Ls[i][k] = fmaf(-lij, Ls[k][j], Ls[i][k]);
     }
     __syncthreads();
   }
   __syncthreads();
   const bool bad = s_fail != 0;
+  // log det of the block: sum log L_jj, in double, one pivot per thread
+  const double ld = block_sum_d((tid < nb && !bad) ? log((double)piv_s[tid]) : 0.0, redd);
   // W = L^-1 by forward substitution, one thread per column c: W[i][c] = (d_ic - sum_k L[i][k] W[k][c]) / L[i][i]
   if (!bad && tid < nb) {
     const int c = tid;

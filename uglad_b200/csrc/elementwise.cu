@@ -11,7 +11,7 @@ int elem_blocks_per_graph(int D) {
   const long long n = (long long)D * D;
   long long b = (n + 2047) / 2048;
   if (b < 1) b = 1;
-  if (b > 64) b = 64;
+  if (b > 512) b = 512;   // D = 1000: 489 blocks, enough to cover the 148 SMs several times
   return (int)b;
 }
 int rho_param_count(int H) { return H * UGLAD_NF + H + H * H + H + H + 1; }
@@ -120,7 +120,7 @@ template <int HT>
 __global__ void __launch_bounds__(EW_THREADS) z_update_bwd_kernel(
     const float* __restrict__ GZ, const float* __restrict__ X, const float* __restrict__ S,
     const float* __restrict__ Tprev, const float* __restrict__ params, int H, int n,
-    float* __restrict__ GX, float* __restrict__ GF3, float* rho_part) {
+    float* __restrict__ GX, float* __restrict__ GF3, float* rho_part, float* __restrict__ GXlo, int D, int ldp) {
   constexpr int HM = RhoMLP<HT>::HM;
   constexpr int NPR_MAX = HM * UGLAD_NF + HM + HM * HM + HM + HM + 1;
   __shared__ float sw[1 + UGLAD_MAX_H * (UGLAD_NF + 4 + UGLAD_MAX_H) + 1 + 64];
@@ -179,7 +179,16 @@ __global__ void __launch_bounds__(EW_THREADS) z_update_bwd_kernel(
       gx = gz + fx;
       gt = ft;
     }
-    GX[base + i] = gx;
+    if (GXlo) {  // split (hi, lo) copy in the padded layout the tcgen05 products read
+      const int r = i / D, c = i - r * D;
+      const size_t o = (size_t)blockIdx.y * D * ldp + (size_t)r * ldp + c;
+      uint32_t hb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(gx));
+      GX[o] = __uint_as_float(hb);
+      GXlo[o] = gx - __uint_as_float(hb);
+    } else {
+      GX[base + i] = gx;
+    }
     GF3[base + i] = gt;
   }
   float* out = rho_part + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * NPR;
@@ -193,13 +202,13 @@ __global__ void __launch_bounds__(EW_THREADS) z_update_bwd_kernel(
 }
 int launch_z_update_bwd(const float* GZ, const float* X, const float* S, const float* Tprev,
                         const float* params, int H, int B, int D, float* GX, float* GF3,
-                        float* rho_part, cudaStream_t st) {
+                        float* rho_part, cudaStream_t st, float* GXlo, int ldp) {
   dim3 grid(elem_blocks_per_graph(D), B);
   const int n = D * D;
   if (H == 3)
-    z_update_bwd_kernel<3><<<grid, EW_THREADS, 0, st>>>(GZ, X, S, Tprev, params, H, n, GX, GF3, rho_part);
+    z_update_bwd_kernel<3><<<grid, EW_THREADS, 0, st>>>(GZ, X, S, Tprev, params, H, n, GX, GF3, rho_part, GXlo, D, ldp);
   else
-    z_update_bwd_kernel<0><<<grid, EW_THREADS, 0, st>>>(GZ, X, S, Tprev, params, H, n, GX, GF3, rho_part);
+    z_update_bwd_kernel<0><<<grid, EW_THREADS, 0, st>>>(GZ, X, S, Tprev, params, H, n, GX, GF3, rho_part, GXlo, D, ldp);
   UGLAD_CHECK_LAUNCH("z_update_bwd_kernel");
   return 0;
 }
@@ -237,6 +246,93 @@ __global__ void __launch_bounds__(EW_THREADS) phi_kernel(
   const float tot = block_sum(tr, red);
   if (threadIdx.x == 0) trh_part[blockIdx.y * gridDim.x + blockIdx.x] = tot;
 }
+// the same on split (hi, lo) operands in the padded [B][D][ldp] layout of the tcgen05 products
+__global__ void __launch_bounds__(EW_THREADS) phi_split_kernel(
+    float* __restrict__ Gh, float* __restrict__ Gl, const float* __restrict__ beta, const float* __restrict__ sroot,
+    const float* __restrict__ snorm, int exact_sqrt, int D, int ldp, float* trh_part) {
+  __shared__ float red[32];
+  const int b = blockIdx.y;
+  const int n = D * D;
+  const float* be = beta + (size_t)b * D;
+  const float* sr = sroot + (size_t)b * D;
+  const float inv_nrm = 1.f / snorm[b];
+  float tr = 0.f;
+  for (int idx = blockIdx.x * EW_THREADS + threadIdx.x; idx < n; idx += gridDim.x * EW_THREADS) {
+    const int i = idx / D, j = idx - i * D;
+    const size_t o = (size_t)b * D * ldp + (size_t)i * ldp + j;
+    const float gt = Gh[o] + Gl[o];
+    float C;
+    if (exact_sqrt)
+      C = 1.f / (sr[i] + sr[j]);
+    else
+      C = 0.5f * ns_backward_factor(sr[i] * inv_nrm, sr[j] * inv_nrm) * inv_nrm;
+    const float Hh = 0.5f * C * gt;
+    if (i == j) tr += Hh;
+    const float w = (be[i] + be[j]) * Hh - 0.5f * gt;
+    uint32_t hb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(w));
+    Gh[o] = __uint_as_float(hb);
+    Gl[o] = w - __uint_as_float(hb);
+  }
+  const float tot = block_sum(tr, red);
+  if (threadIdx.x == 0) trh_part[blockIdx.y * gridDim.x + blockIdx.x] = tot;
+}
+int launch_phi_split(float* Gh, float* Gl, const float* beta, const float* sroot, const float* snorm,
+                     int exact_sqrt, int B, int D, int ldp, float* trh_part, cudaStream_t st) {
+  dim3 grid(elem_blocks_per_graph(D), B);
+  phi_split_kernel<<<grid, EW_THREADS, 0, st>>>(Gh, Gl, beta, sroot, snorm, exact_sqrt, D, ldp, trh_part);
+  UGLAD_CHECK_LAUNCH("phi_split_kernel");
+  return 0;
+}
+
+// Eigenvectors for the tcgen05 products: Vt [B][D][D] (row k = eigenvector k) ->
+//   Vt split, V = Vt^T split, and (optionally) VF = V diag(f) split, all [B][D][ldp].
+// 32x32 tiles through shared memory, block (32, 8).
+__global__ void eigvec_split_kernel(const float* __restrict__ Vt, const float* __restrict__ f, int D, int ldp,
+                                    float* __restrict__ Th, float* __restrict__ Tl, float* __restrict__ Vh,
+                                    float* __restrict__ Vl, float* __restrict__ Fh, float* __restrict__ Fl) {
+  __shared__ float t[32][33];
+  const size_t base = (size_t)blockIdx.z * D * D, pbase = (size_t)blockIdx.z * D * ldp;
+  const int k0 = blockIdx.y * 32, i0 = blockIdx.x * 32;   // tile of Vt: rows k0.., columns i0..
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int k = k0 + r, i = i0 + threadIdx.x;
+    float v = 0.f;
+    if (k < D && i < D) {
+      v = Vt[base + (size_t)k * D + i];
+      uint32_t hb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+      Th[pbase + (size_t)k * ldp + i] = __uint_as_float(hb);
+      Tl[pbase + (size_t)k * ldp + i] = v - __uint_as_float(hb);
+    }
+    t[r][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int i = i0 + r, k = k0 + threadIdx.x;   // V[i][k] = Vt[k][i]
+    if (i < D && k < D) {
+      const float v = t[threadIdx.x][r];
+      uint32_t hb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+      Vh[pbase + (size_t)i * ldp + k] = __uint_as_float(hb);
+      Vl[pbase + (size_t)i * ldp + k] = v - __uint_as_float(hb);
+      if (Fh) {
+        const float w = v * f[(size_t)blockIdx.z * D + k];
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(w));
+        Fh[pbase + (size_t)i * ldp + k] = __uint_as_float(hb);
+        Fl[pbase + (size_t)i * ldp + k] = w - __uint_as_float(hb);
+      }
+    }
+  }
+}
+int launch_eigvec_split(const float* Vt, const float* f, int B, int D, int ldp, float* Th, float* Tl, float* Vh,
+                        float* Vl, float* Fh, float* Fl, cudaStream_t st) {
+  const int nt = (D + 31) / 32;
+  dim3 grid(nt, nt, B), blk(32, 8);
+  eigvec_split_kernel<<<grid, blk, 0, st>>>(Vt, f, D, ldp, Th, Tl, Vh, Vl, Fh, Fl);
+  UGLAD_CHECK_LAUNCH("eigvec_split_kernel");
+  return 0;
+}
+
 int launch_phi(float* Gt, const float* beta, const float* sroot, const float* snorm,
                const float* lam, int exact_sqrt, int B, int D, float* trh_part, cudaStream_t st) {
   (void)lam;
@@ -395,30 +491,37 @@ int launch_finalize_grads(const float* params, int H, int L, int nblk, const flo
 }
 
 // ------------------------------------------------------------------------------------------
-// loss_b = -logdet_b + <S_b, theta_b>  (main.py:307-315); the last block sums over graphs.
+// loss_b = -logdet_b + <S_b, theta_b>  (main.py:307-315).  grid (blocks per graph, B): per-block
+// partials of <S, theta>; the last block to finish sums them per graph and over graphs in double.
 __global__ void __launch_bounds__(EW_THREADS) loss_terms_kernel(
     const float* __restrict__ theta, const float* __restrict__ S, long long strideS,
-    const float* __restrict__ logdet, int n, float Bdiv, float* lossb, float* loss_out,
+    const float* __restrict__ logdet, int n, float Bdiv, float* part, float* lossb, float* loss_out,
     unsigned* counter) {
   __shared__ double redd[32];
   __shared__ bool s_last;
-  const int b = blockIdx.x;
+  const int b = blockIdx.y, nb = gridDim.x, B = gridDim.y;
   const float* T = theta + (size_t)b * n;
   const float* Sb = S + (size_t)b * strideS;
   double acc = 0.0;
-  for (int i = threadIdx.x; i < n; i += EW_THREADS) acc += (double)Sb[i] * (double)T[i];
+  for (int i = blockIdx.x * EW_THREADS + threadIdx.x; i < n; i += nb * EW_THREADS) acc += (double)Sb[i] * (double)T[i];
   acc = block_sum_d(acc, redd);
   if (threadIdx.x == 0) {
-    lossb[b] = (float)(acc - (double)logdet[b]);
+    part[(size_t)b * nb + blockIdx.x] = (float)acc;
     __threadfence();
     const unsigned ticket = atomicAdd(counter, 1u);
-    s_last = (ticket == gridDim.x - 1);
+    s_last = (ticket == (unsigned)(nb * B) - 1u);
   }
   __syncthreads();
   if (s_last) {
     __threadfence();
     double s = 0.0;
-    for (unsigned i = threadIdx.x; i < gridDim.x; i += EW_THREADS) s += (double)((volatile float*)lossb)[i];
+    for (int g = threadIdx.x; g < B; g += EW_THREADS) {
+      double t = 0.0;
+      for (int i = 0; i < nb; ++i) t += (double)((volatile float*)part)[(size_t)g * nb + i];
+      const float lb = (float)(t - (double)logdet[g]);
+      lossb[g] = lb;
+      s += (double)lb;
+    }
     s = block_sum_d(s, redd);
     if (threadIdx.x == 0) {
       loss_out[0] = (float)(s / (double)Bdiv);
@@ -426,10 +529,16 @@ __global__ void __launch_bounds__(EW_THREADS) loss_terms_kernel(
     }
   }
 }
+int loss_blocks_per_graph(int D) {
+  long long nb = ((long long)D * D + 8191) / 8192;
+  if (nb > 128) nb = 128;
+  return (int)(nb < 1 ? 1 : nb);
+}
 int launch_loss_terms(const float* theta, const float* S, long long strideS, const float* logdet,
-                      int B, int D, float Bdiv, float* lossb, float* loss_out, unsigned* counter,
+                      int B, int D, float Bdiv, float* part, float* lossb, float* loss_out, unsigned* counter,
                       cudaStream_t st) {
-  loss_terms_kernel<<<B, EW_THREADS, 0, st>>>(theta, S, strideS, logdet, D * D, Bdiv, lossb, loss_out, counter);
+  dim3 grid(loss_blocks_per_graph(D), B);
+  loss_terms_kernel<<<grid, EW_THREADS, 0, st>>>(theta, S, strideS, logdet, D * D, Bdiv, part, lossb, loss_out, counter);
   UGLAD_CHECK_LAUNCH("loss_terms_kernel");
   return 0;
 }

@@ -125,7 +125,12 @@ int launch_z_update_fwd(const float* X, const float* S, const float* Tprev, cons
                         unsigned* counter, cudaStream_t st);
 int launch_z_update_bwd(const float* GZ, const float* X, const float* S, const float* Tprev,
                         const float* params, int H, int B, int D, float* GX, float* GF3,
-                        float* rho_part, cudaStream_t st);
+                        float* rho_part, cudaStream_t st, float* GXlo = nullptr, int ldp = 0);
+int launch_phi_split(float* Gh, float* Gl, const float* beta, const float* sroot, const float* snorm,
+                     int exact_sqrt, int B, int D, int ldp, float* trh_part, cudaStream_t st);
+int launch_eigvec_split(const float* Vt, const float* f, int B, int D, int ldp, float* Th, float* Tl, float* Vh,
+                        float* Vl, float* Fh, float* Fl, cudaStream_t st);
+bool ns_use_tc();
 int launch_phi(float* Gt, const float* beta, const float* sroot, const float* snorm,
                const float* lam, int exact_sqrt, int B, int D, float* trh_part, cudaStream_t st);
 int launch_gb_finish(const float* Gb, const float* GF3, const float* S, int B, int D, float* Gnext,
@@ -139,8 +144,9 @@ int launch_finalize_grads(const float* params, int H, int L, int nblk, const flo
                           const float* trh_part, const float* sgb_part, const float* t0_part,
                           const float* lam, const float* lamfeat, float* grad_params,
                           cudaStream_t st);
+int loss_blocks_per_graph(int D);
 int launch_loss_terms(const float* theta, const float* S, long long strideS, const float* logdet,
-                      int B, int D, float Bdiv, float* lossb, float* loss_out, unsigned* counter,
+                      int B, int D, float Bdiv, float* part, float* lossb, float* loss_out, unsigned* counter,
                       cudaStream_t st);
 int launch_colmean(const float* X, int B, int M, int D, float* mean, cudaStream_t st);
 int launch_condition(float* S, float* wS, int B, int D, float offset, cudaStream_t st);

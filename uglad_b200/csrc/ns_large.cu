@@ -174,6 +174,7 @@ struct NsBuf {
 static inline size_t al4(size_t x) { return (x + 3) & ~(size_t)3; }
 
 static int g_use_tc = 1;
+bool ns_use_tc() { return g_use_tc != 0; }
 int ns_tune(const char* key, int value) {
   if (!strcmp(key, "use_tc")) { g_use_tc = value ? 1 : 0; return 0; }
   if (!strcmp(key, "tc_bn")) return tc_tune_bn(value);

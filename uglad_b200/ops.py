@@ -250,7 +250,7 @@ def z_update(X, S, theta_prev, flat_params, H=3):
     B, D, _ = X.shape
     Z = torch.empty_like(X)
     normf = torch.empty(1, device=X.device, dtype=torch.float32)
-    scratch = torch.empty(64 * B + 16, device=X.device, dtype=torch.float32)
+    scratch = torch.empty(512 * B + 16, device=X.device, dtype=torch.float32)
     check(lib.uglad_z_update(_ptr(X), _ptr(S), _ptr(theta_prev), _ptr(flat_params), H, B, D, _ptr(Z),
                              _ptr(normf), _ptr(scratch), _stream(X)), "uglad_z_update")
     return Z, normf
