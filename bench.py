@@ -109,6 +109,10 @@ def cpu_oracle_rate(B, D, M, seed, steps, warmup, max_graphs):
     oracle/uglad_oracle.py) on the host cores, bounded sample of the same workload."""
     import torch
     from oracle import uglad_oracle as O
+    try:  # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it may
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        pass
     nb = min(B, max_graphs)
     X = synth(nb, D, M, seed)
     S = torch.tensor(O.covariance(X), dtype=torch.float32)
@@ -156,6 +160,9 @@ def run_reference(args, wl, rank, world):
 
 # ------------------------------------------------------------------------------------------
 KERNELS = ((0, "eig_jacobi_small_kernel"), (1, "tc_gemm_kernel"))
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
+# (profiles/r01_ncu_full_*.txt), keyed by (kernel, graphs, D); bytes
+NCU_TRAFFIC = {("eig", 256, 100): 30.8e6, ("tc", 1, 1000): 16.1e6}
 
 
 def time_gpu_workload(name, steps, warmup, rank, world, group, dev, profile=False):
@@ -250,7 +257,8 @@ def roofline_of(r, peaks):
             peak, src = 1400.0, "fallback (B200_PROFILING.md sustained bf16)"
         achieved = tcg["work"] / (tcg["ms"] * 1e-3) / 1e12
         return {"bound": "tensor", "kernel": "tc_gemm_kernel (tcgen05.mma kind::tf32, 3xTF32 split operands)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": NCU_TRAFFIC.get(("tc", r["B"], r["D"])),
                 "peak_source": src, "avg_launch_ms": tcg["ms"] / tcg["launches"],
                 "launches_per_step": tcg["launches"] / prof["steps"], "kernel_share_of_step": tcg["ms"] / step_ms,
                 "tf32_pipe_frac": 3.0 * achieved / (peak / 2.0),
@@ -263,7 +271,8 @@ def roofline_of(r, peaks):
         peak, src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = eig["work"] / (eig["ms"] * 1e-3) / 1e9 if eig["launches"] else None
     return {"bound": "hbm", "kernel": "eig_jacobi_small_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": src,
+            "frac": (achieved / peak) if achieved else None, "traffic": NCU_TRAFFIC.get(("eig", r["B"], r["D"])),
+            "peak_source": src,
             "avg_launch_ms": (eig["ms"] / eig["launches"]) if eig["launches"] else None,
             "launches_per_step": eig["launches"] / prof["steps"],
             "kernel_share_of_step": eig["ms"] / step_ms,
@@ -321,8 +330,12 @@ def main():
     if rank == 0:
         D, B = r["D"], r["B"]
         big = D >= 500
-        cpu_rate, cpu_ms, cpu_nb, cores = cpu_oracle_rate(spec["B"], spec["D"], spec["M"], 1234, 1 if big else 2,
-                                                          0 if big else 1, max_graphs=32)
+        cpu = None
+        if world == 1:  # the CPU baseline is reported at N=1 only
+            cpu_rate, cpu_ms, cpu_nb, cores = cpu_oracle_rate(spec["B"], spec["D"], spec["M"], 1234, 1 if big else 2,
+                                                              0 if big else 1, max_graphs=32)
+            cpu = {"value": cpu_rate, "unit": "layer-graphs/s", "cores": cores, "kind": "port",
+                   "sample": f"{cpu_nb} of {spec['B']} graphs per step (oracle port, torch CPU)"}
         line = {
             "metric": "unrolled-layer-graphs/sec fwd+bwd", "value": r["value"], "unit": "layer-graphs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
@@ -336,8 +349,7 @@ def main():
                     "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
             "gpu_launches": r["launches"],
             "roofline": roofline_of(r, peaks),
-            "cpu_baseline": {"value": cpu_rate, "unit": "layer-graphs/s", "cores": cores, "kind": "port",
-                             "sample": f"{cpu_nb} of {spec['B']} graphs per step (oracle port, torch CPU)"},
+            "cpu_baseline": cpu,
             "extra": extra,
         }
         print(json.dumps(line), flush=True)
