@@ -58,6 +58,14 @@ __device__ __forceinline__ float group_sum(float v) {
   return v;
 }
 
+// same, but only the LP lanes of this group take part (divergent trip counts across groups)
+template <int LP>
+__device__ __forceinline__ float group_sum_masked(float v, unsigned mask) {
+#pragma unroll
+  for (int o = LP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+  return v;
+}
+
 __device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
 }
@@ -92,7 +100,9 @@ constexpr int eig_max_threads(int LP, int CH) {
   return want > cap ? cap : want;
 }
 
-template <int LP, int CH>
+// PAD: the launcher padded the shared-memory columns to ld = LP * CH * 4 floats (zero rows beyond
+// D), so every lane's CH chunks exist and the chunk loops carry no predicates.
+template <int LP, int CH, bool PAD>
 __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_kernel(EigArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int D = a.D, ld = a.ld;
@@ -128,6 +138,7 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
 
   int sweeps = 0;
   float sigma = 0.f, trace = 0.f, wsum = 0.f;
+  long long t_start = clock64(), t_sweeps0 = 0, t_sweeps1 = 0;
   for (int attempt = 0; attempt < 2; ++attempt) {
     // ---- load (coalesced along the contiguous global dimension) -------------------------
     float trace_part = 0.f, fro_part = 0.f;
@@ -219,6 +230,7 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
     }
 
     // ---- Jacobi sweeps -------------------------------------------------------------------
+    t_sweeps0 = clock64();
     for (int sweep = 0; sweep < a.max_sweeps; ++sweep) {
       // refresh the cached squared norms
       for (int cb = 0; cb < D; cb += ngroups) {
@@ -240,79 +252,143 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
       }
       __syncthreads();
       float wmax = 0.f;
-      for (int r = 0; r < m; ++r) {
-        for (int pb = 0; pb < npairs; pb += ngroups) {
-          const int pi = pb + grp;
-          int p = 0, q = 0;
-          bool valid = pi < npairs;
-          if (valid) {
-            rr_pair(n, r, pi, p, q);
-            valid = (p < D) && (q < D);  // padding player of an odd D
-          }
-          float* up = U + (size_t)p * ld;
-          float* uq = U + (size_t)q * ld;
-          float4 av[CH], bv[CH];
-          float ga = 0.f;
+      const float tol2 = tol * tol;
+      float* const Ul = U + 4 * gl;
+      // one column pair: dot product, convergence test, rotation.  `valid` pairs only are written.
+      auto do_pair = [&](int p, int q, bool valid) {
+        float* up = Ul + (size_t)p * ld;
+        float* uq = Ul + (size_t)q * ld;
+        float4 av[CH], bv[CH];
+        float g0 = 0.f, g1 = 0.f;   // two independent chains halve the dependent-FFMA latency
 #pragma unroll
-          for (int c = 0; c < CH; ++c) {
-            const int ch = gl + LP * c;
-            if (valid && ch < nch) {
-              av[c] = *reinterpret_cast<const float4*>(up + 4 * ch);
-              bv[c] = *reinterpret_cast<const float4*>(uq + 4 * ch);
-              ga = dot4(av[c], bv[c], ga);
-            } else {
-              av[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-              bv[c] = av[c];
-            }
-          }
-          ga = group_sum<LP>(ga);
-          if (valid) {
-            const float al = nrm2[p], be = nrm2[q];
-            const float den = al * be;
-            const float off = (den > 0.f) ? fabsf(ga) * rsqrtf(den) : 0.f;
-            wmax = fmaxf(wmax, off);
-            if (off > tol) {
-              const float d = be - al, g2 = 2.f * ga;
-              const float h = sqrtf(fmaf(d, d, g2 * g2));
-              float t = __fdividef(fabsf(g2), fabsf(d) + h);
-              t = ((d < 0.f) != (g2 < 0.f)) ? -t : t;
-              const float x = fmaf(t, t, 1.f);
-              float cs = rsqrtf(x);
-              cs = cs * fmaf(-0.5f * x, cs * cs, 1.5f);  // one Newton step: ~0.5 ulp
-              const float sn = t * cs;
-              const float tau = __fdividef(sn, 1.f + cs);
-#pragma unroll
-              for (int c = 0; c < CH; ++c) {
-                const int ch = gl + LP * c;
-                if (ch < nch) {
-                  float4 na, nb;
-                  na.x = av[c].x - sn * fmaf(tau, av[c].x, bv[c].x);  nb.x = bv[c].x + sn * fmaf(-tau, bv[c].x, av[c].x);
-                  na.y = av[c].y - sn * fmaf(tau, av[c].y, bv[c].y);  nb.y = bv[c].y + sn * fmaf(-tau, bv[c].y, av[c].y);
-                  na.z = av[c].z - sn * fmaf(tau, av[c].z, bv[c].z);  nb.z = bv[c].z + sn * fmaf(-tau, bv[c].z, av[c].z);
-                  na.w = av[c].w - sn * fmaf(tau, av[c].w, bv[c].w);  nb.w = bv[c].w + sn * fmaf(-tau, bv[c].w, av[c].w);
-                  *reinterpret_cast<float4*>(up + 4 * ch) = na;
-                  *reinterpret_cast<float4*>(uq + 4 * ch) = nb;
-                }
-              }
-              if (gl == 0) {
-                nrm2[p] = fmaxf(fmaf(-t, ga, al), 0.f);
-                nrm2[q] = fmaf(t, ga, be);
-              }
-            }
+        for (int c = 0; c < CH; ++c) {
+          if (PAD || gl + LP * c < nch) {
+            av[c] = *reinterpret_cast<const float4*>(up + 4 * LP * c);
+            bv[c] = *reinterpret_cast<const float4*>(uq + 4 * LP * c);
+            g0 = fmaf(av[c].x, bv[c].x, fmaf(av[c].y, bv[c].y, g0));
+            g1 = fmaf(av[c].z, bv[c].z, fmaf(av[c].w, bv[c].w, g1));
+          } else {
+            av[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            bv[c] = av[c];
           }
         }
-        __syncthreads();
+        const float ga = group_sum<LP>(g0 + g1);
+        const float al = nrm2[p], be = nrm2[q];
+        const float den = al * be;
+        const float g2s = ga * ga;
+        // |cos(u_p, u_q)| > tol  <=>  ga^2 > tol^2 |u_p|^2 |u_q|^2  (no rsqrt on the common path)
+        if (valid && g2s > tol2 * den) {
+          wmax = fmaxf(wmax, g2s / den);
+          const float d = be - al, g2 = 2.f * ga;
+          const float h = sqrtf(fmaf(d, d, g2 * g2));
+          float t = __fdividef(fabsf(g2), fabsf(d) + h);
+          t = ((d < 0.f) != (g2 < 0.f)) ? -t : t;
+          const float x = fmaf(t, t, 1.f);
+          float cs = rsqrtf(x);
+          cs = cs * fmaf(-0.5f * x, cs * cs, 1.5f);  // one Newton step: ~0.5 ulp
+          const float sn = t * cs;
+          const float tau = __fdividef(sn, 1.f + cs);
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            if (PAD || gl + LP * c < nch) {
+              float4 na, nb;
+              na.x = av[c].x - sn * fmaf(tau, av[c].x, bv[c].x);  nb.x = bv[c].x + sn * fmaf(-tau, bv[c].x, av[c].x);
+              na.y = av[c].y - sn * fmaf(tau, av[c].y, bv[c].y);  nb.y = bv[c].y + sn * fmaf(-tau, bv[c].y, av[c].y);
+              na.z = av[c].z - sn * fmaf(tau, av[c].z, bv[c].z);  nb.z = bv[c].z + sn * fmaf(-tau, bv[c].z, av[c].z);
+              na.w = av[c].w - sn * fmaf(tau, av[c].w, bv[c].w);  nb.w = bv[c].w + sn * fmaf(-tau, bv[c].w, av[c].w);
+              *reinterpret_cast<float4*>(up + 4 * LP * c) = na;
+              *reinterpret_cast<float4*>(uq + 4 * LP * c) = nb;
+            }
+          }
+          if (gl == 0) {
+            nrm2[p] = fmaxf(fmaf(-t, ga, al), 0.f);
+            nrm2[q] = fmaf(t, ga, be);
+          }
+        }
+      };
+      if (ngroups >= npairs) {
+        // every pair of a round has its own lane group: the pair indices advance incrementally
+        const bool act = grp < npairs;
+        int p = 0, q = 0;
+        if (act) rr_pair(n, 0, grp, p, q);
+        for (int r = 0; r < m; ++r) {
+          const bool valid = act && p < D && q < D;  // padding player of an odd D
+          do_pair(valid ? p : 0, valid ? q : 0, valid);
+          __syncthreads();
+          if (grp == 0) {
+            q = r + 1;
+          } else {
+            p = (p + 1 == m) ? 0 : p + 1;
+            q = (q + 1 == m) ? 0 : q + 1;
+          }
+        }
+      } else {
+        for (int r = 0; r < m; ++r) {
+          for (int pb = 0; pb < npairs; pb += ngroups) {
+            const int pi = pb + grp;
+            int p = 0, q = 0;
+            bool valid = pi < npairs;
+            if (valid) {
+              rr_pair(n, r, pi, p, q);
+              valid = (p < D) && (q < D);
+            }
+            do_pair(valid ? p : 0, valid ? q : 0, valid);
+          }
+          __syncthreads();
+        }
       }
       ++sweeps;
       wmax = warp_max(wmax);
       if (lane == 0) atomicMax(&s_flag, __float_as_uint(wmax));
       __syncthreads();
-      const float fmaxoff = __uint_as_float(s_flag);
+      const float fmaxoff = __uint_as_float(s_flag);   // largest squared cosine above tol^2, 0 if none
       __syncthreads();
       if (tid == 0) s_flag = 0u;
-      if (fmaxoff <= tol) break;
+      if (fmaxoff <= 0.f) break;
+      // Barrier-free check of all D(D-1)/2 cosines (no writes): when the sweep above already
+      // converged the columns this replaces a whole no-rotation sweep of m synchronised rounds.
+      {
+        float cmax = 0.f;
+        const unsigned gmask = (LP >= 32) ? 0xffffffffu : (((1u << LP) - 1u) << (lane & ~(LP - 1)));
+        for (int pp = grp; pp < (D + 1) / 2; pp += ngroups) {
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {   // rows pp and D-1-pp together: balanced work
+            const int p = half ? D - 1 - pp : pp;
+            if (half && p == pp) break;
+            const float* up = Ul + (size_t)p * ld;
+            float4 av[CH];
+#pragma unroll
+            for (int c = 0; c < CH; ++c)
+              av[c] = (PAD || gl + LP * c < nch) ? *reinterpret_cast<const float4*>(up + 4 * LP * c)
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float al = nrm2[p];
+            for (int q = p + 1; q < D; ++q) {
+              const float* uq = Ul + (size_t)q * ld;
+              float g0 = 0.f, g1 = 0.f;
+#pragma unroll
+              for (int c = 0; c < CH; ++c) {
+                if (PAD || gl + LP * c < nch) {
+                  const float4 bv = *reinterpret_cast<const float4*>(uq + 4 * LP * c);
+                  g0 = fmaf(av[c].x, bv.x, fmaf(av[c].y, bv.y, g0));
+                  g1 = fmaf(av[c].z, bv.z, fmaf(av[c].w, bv.w, g1));
+                }
+              }
+              const float ga = group_sum_masked<LP>(g0 + g1, gmask);
+              const float den = al * nrm2[q];
+              if (ga * ga > tol2 * den) cmax = 1.f;
+            }
+          }
+        }
+        if (cmax > 0.f) atomicMax(&s_flag, __float_as_uint(cmax));
+        __syncthreads();
+        const bool more = __uint_as_float(s_flag) > 0.f;
+        __syncthreads();
+        if (tid == 0) s_flag = 0u;
+        if (!more) break;
+      }
     }
 
+    t_sweeps1 = clock64();
     // ---- column norms ----------------------------------------------------------------------
     float wsum_part = 0.f;
     for (int col = warp; col < D; col += nwarps) {
@@ -380,6 +456,11 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
     o[1] = sigma;
     o[2] = trace;
     o[3] = wsum;
+    if (a.timing) {  // developer knob "eig_timing": phase cycle counts instead of shift / trace / sum
+      o[1] = (float)(t_sweeps0 - t_start);
+      o[2] = (float)(t_sweeps1 - t_sweeps0);
+      o[3] = (float)(clock64() - t_sweeps1);
+    }
   }
   __syncthreads();
 
@@ -435,23 +516,27 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
 
 static int g_tune_lp = 0;      // 0 = auto; otherwise force lanes per column pair (4/8/16/32)
 static int g_tune_keepg = -1;  // -1 = auto (keep G when two buffers fit); 0 / 1 force
+static int g_tune_timing = 0;
+static int g_tune_pad = 1;     // 1 = pad shared-memory columns to LP*CH*4 floats when it fits
 int eig_small_tune(const char* key, int value) {
   if (!strcmp(key, "eig_lp")) { g_tune_lp = value; return 0; }
   if (!strcmp(key, "eig_keepg")) { g_tune_keepg = value; return 0; }
+  if (!strcmp(key, "eig_pad")) { g_tune_pad = value; return 0; }
+  if (!strcmp(key, "eig_timing")) { g_tune_timing = value; return 0; }
   return 1;
 }
 
-template <int LP, int CH>
+template <int LP, int CH, bool PAD>
 static int launch_cfg(const EigArgs& a, int B, size_t smem, cudaStream_t st) {
   const int npairs = (a.D + 1) / 2;
   int threads = ((npairs * LP + 31) / 32) * 32;
   if (threads > eig_max_threads(LP, CH)) threads = eig_max_threads(LP, CH);
   if (threads < 128) threads = 128;
   if (threads < a.D) threads = ((a.D + 31) / 32) * 32;  // the power iteration wants a thread per row
-  UGLAD_CUDA(cudaFuncSetAttribute(eig_jacobi_small_kernel<LP, CH>,
+  UGLAD_CUDA(cudaFuncSetAttribute(eig_jacobi_small_kernel<LP, CH, PAD>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   profile_begin(st, 0, (double)B * (4.0 * a.D * a.D + 3.0 * a.D) * 4.0);
-  eig_jacobi_small_kernel<LP, CH><<<B, threads, smem, st>>>(a);
+  eig_jacobi_small_kernel<LP, CH, PAD><<<B, threads, smem, st>>>(a);
   profile_end(st);
   UGLAD_CHECK_LAUNCH("eig_jacobi_small_kernel");
   return 0;
@@ -459,25 +544,41 @@ static int launch_cfg(const EigArgs& a, int B, size_t smem, cudaStream_t st) {
 
 int launch_eig_small(const EigArgs& a_in, int B, cudaStream_t st) {
   EigArgs a = a_in;
+  a.timing = g_tune_timing;
   a.ld = (a.D + 3) & ~3;
   if (a.D > UGLAD_SMALL_D_MAX) {
     set_error("eig_small: D=%d exceeds the shared-memory solver limit %d", a.D, UGLAD_SMALL_D_MAX);
     return 1;
   }
-  const size_t mat = (size_t)a.ld * a.D * sizeof(float);
-  const size_t extra = 2 * a.ld * sizeof(float) + 32 * sizeof(double) + 32 * sizeof(float) + 16;
-  const bool fits2 = 2 * mat + extra <= 227 * 1024;
-  a.keepG = (g_tune_keepg < 0) ? (fits2 ? 1 : 0) : (g_tune_keepg && fits2 ? 1 : 0);
-  if (!a.keepG) a.warmVt = nullptr;
-  const size_t smem = (a.keepG ? 2 : 1) * mat + extra;
-  const int nch = a.ld / 4;
+  int nch = a.ld / 4;
   // lanes per column pair: narrow groups replicate the rotation scalar math less (the kernel
   // is issue-bound), wide groups shorten the per-round dependent chain.
   int lp = g_tune_lp;
   if (lp == 0) lp = (nch <= 8) ? 4 : (nch <= 32 ? 8 : 16);
   while (lp < 32 && lp * 8 < nch) lp *= 2;
   const int ch = (nch + lp - 1) / lp;
-#define UGLAD_EIG_CASE(LP_, CH_) if (lp == LP_ && ch <= CH_) return launch_cfg<LP_, CH_>(a, B, smem, st)
+  // the template CH that the case list below will pick for (lp, ch)
+  int chT = ch <= 1 ? 1 : (ch <= 2 ? 2 : (ch <= 4 ? 4 : 8));
+  if (lp == 4 && chT < 2) chT = 2;
+  auto fits = [&](int ld, int nbuf) {
+    const size_t mat = (size_t)ld * a.D * sizeof(float);
+    const size_t extra = 2 * ld * sizeof(float) + 32 * sizeof(double) + 32 * sizeof(float) + 16;
+    return nbuf * mat + extra <= 227 * 1024;
+  };
+  // padded columns (branch-free chunk loops) when that does not cost the second buffer
+  const int ld_pad = lp * chT * 4;
+  const bool want2 = fits(a.ld, 2);
+  bool pad = g_tune_pad != 0 && chT <= 4 && fits(ld_pad, want2 ? 2 : 1);
+  if (pad) a.ld = ld_pad;
+  const size_t mat = (size_t)a.ld * a.D * sizeof(float);
+  const size_t extra = 2 * a.ld * sizeof(float) + 32 * sizeof(double) + 32 * sizeof(float) + 16;
+  const bool fits2 = 2 * mat + extra <= 227 * 1024;
+  a.keepG = (g_tune_keepg < 0) ? (fits2 ? 1 : 0) : (g_tune_keepg && fits2 ? 1 : 0);
+  if (!a.keepG) a.warmVt = nullptr;
+  const size_t smem = (a.keepG ? 2 : 1) * mat + extra;
+#define UGLAD_EIG_CASE(LP_, CH_)                                                    \
+  if (lp == LP_ && ch <= CH_)                                                       \
+    return pad ? launch_cfg<LP_, CH_, true>(a, B, smem, st) : launch_cfg<LP_, CH_, false>(a, B, smem, st)
   UGLAD_EIG_CASE(4, 2); UGLAD_EIG_CASE(4, 4); UGLAD_EIG_CASE(4, 8);
   UGLAD_EIG_CASE(8, 1); UGLAD_EIG_CASE(8, 2); UGLAD_EIG_CASE(8, 4); UGLAD_EIG_CASE(8, 8);
   UGLAD_EIG_CASE(16, 1); UGLAD_EIG_CASE(16, 2); UGLAD_EIG_CASE(16, 4);
