@@ -192,7 +192,8 @@ def time_gpu_workload(name, steps, warmup, rank, world, group, dev, profile=Fals
 
     def step(Sb):
         opt.zero_grad()
-        _, loss = ug.forward_uGLAD(Sb, model, L=L_LAYERS, INIT_DIAG=0, group=group if world > 1 else None)
+        _, loss = ug.forward_uGLAD(Sb, model, L=L_LAYERS, INIT_DIAG=0, group=group if world > 1 else None,
+                                   total_graphs=B * world)
         loss.backward()
         opt.step()
         return loss

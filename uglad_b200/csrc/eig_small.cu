@@ -95,6 +95,34 @@ __device__ __forceinline__ void group_matvec(const float* __restrict__ G, const 
   }
 }
 
+// two columns at once: the G chunks are loaded once for both (half the shared-memory traffic per FMA)
+template <int LP, int CH>
+__device__ __forceinline__ void group_matvec2(const float* __restrict__ G, const float* __restrict__ u0,
+                                              const float* __restrict__ u1, int D, int ld, int nch, int gl,
+                                              float4* t0, float4* t1) {
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    t0[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    t1[c] = t0[c];
+  }
+#pragma unroll 4
+  for (int j = 0; j < D; ++j) {
+    const float v0 = u0[j], v1 = u1[j];
+    const float* gj = G + (size_t)j * ld;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int ch = gl + LP * c;
+      if (ch < nch) {
+        const float4 g4 = *reinterpret_cast<const float4*>(gj + 4 * ch);
+        t0[c].x = fmaf(g4.x, v0, t0[c].x);  t1[c].x = fmaf(g4.x, v1, t1[c].x);
+        t0[c].y = fmaf(g4.y, v0, t0[c].y);  t1[c].y = fmaf(g4.y, v1, t1[c].y);
+        t0[c].z = fmaf(g4.z, v0, t0[c].z);  t1[c].z = fmaf(g4.z, v1, t1[c].z);
+        t0[c].w = fmaf(g4.w, v0, t0[c].w);  t1[c].w = fmaf(g4.w, v1, t1[c].w);
+      }
+    }
+  }
+}
+
 constexpr int eig_max_threads(int LP, int CH) {
   const int want = (116 * LP + 31) / 32 * 32, cap = (CH >= 8) ? 512 : 1024;  // CH=8 needs >64 registers
   return want > cap ? cap : want;
@@ -209,17 +237,36 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
           U[idx] = (row < D) ? Vp[(size_t)col * D + row] : 0.f;
         }
         __syncthreads();
-        for (int cb = 0; cb < D; cb += ngroups) {
-          const int col = cb + grp;
-          float4 tv[CH];
-          float* u = U + (size_t)(col < D ? col : 0) * ld;
-          group_matvec<LP, CH>(Gk, u, D, ld, nch, gl, tv);
-          __syncwarp();
-          if (col < D) {
+        if constexpr (CH <= 4) {
+          for (int cb = 0; cb < D; cb += 2 * ngroups) {
+            const int c0 = cb + 2 * grp, c1 = c0 + 1;
+            float4 t0[CH], t1[CH];
+            float* u0 = U + (size_t)(c0 < D ? c0 : 0) * ld;
+            float* u1 = U + (size_t)(c1 < D ? c1 : 0) * ld;
+            group_matvec2<LP, CH>(Gk, u0, u1, D, ld, nch, gl, t0, t1);
+            __syncwarp();
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
               const int ch = gl + LP * c;
-              if (ch < nch) *reinterpret_cast<float4*>(u + 4 * ch) = tv[c];
+              if (ch < nch) {
+                if (c0 < D) *reinterpret_cast<float4*>(u0 + 4 * ch) = t0[c];
+                if (c1 < D) *reinterpret_cast<float4*>(u1 + 4 * ch) = t1[c];
+              }
+            }
+          }
+        } else {
+          for (int cb = 0; cb < D; cb += ngroups) {
+            const int col = cb + grp;
+            float4 tv[CH];
+            float* u = U + (size_t)(col < D ? col : 0) * ld;
+            group_matvec<LP, CH>(Gk, u, D, ld, nch, gl, tv);
+            __syncwarp();
+            if (col < D) {
+#pragma unroll
+              for (int c = 0; c < CH; ++c) {
+                const int ch = gl + LP * c;
+                if (ch < nch) *reinterpret_cast<float4*>(u + 4 * ch) = tv[c];
+              }
             }
           }
         }
@@ -421,24 +468,51 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
   __syncthreads();
   if (a.keepG) {
     // Rayleigh quotients with the kept G = A + sigma I: lambda_k = u^T G u / u^T u - sigma
-    for (int cb = 0; cb < D; cb += ngroups) {
-      const int col = cb + grp;
-      const float* u = U + (size_t)(col < D ? col : 0) * ld;
-      float4 tv[CH];
-      group_matvec<LP, CH>(Gk, u, D, ld, nch, gl, tv);
-      float num = 0.f, den = 0.f;
+    if constexpr (CH <= 4) {
+      for (int cb = 0; cb < D; cb += 2 * ngroups) {
+        const int c0 = cb + 2 * grp, c1 = c0 + 1;
+        const float* u0 = U + (size_t)(c0 < D ? c0 : 0) * ld;
+        const float* u1 = U + (size_t)(c1 < D ? c1 : 0) * ld;
+        float4 t0[CH], t1[CH];
+        group_matvec2<LP, CH>(Gk, u0, u1, D, ld, nch, gl, t0, t1);
+        float n0 = 0.f, d0 = 0.f, n1 = 0.f, d1 = 0.f;
 #pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        const int ch = gl + LP * c;
-        if (ch < nch) {
-          const float4 uv = *reinterpret_cast<const float4*>(u + 4 * ch);
-          num = dot4(tv[c], uv, num);
-          den = dot4(uv, uv, den);
+        for (int c = 0; c < CH; ++c) {
+          const int ch = gl + LP * c;
+          if (ch < nch) {
+            const float4 a0 = *reinterpret_cast<const float4*>(u0 + 4 * ch);
+            const float4 a1 = *reinterpret_cast<const float4*>(u1 + 4 * ch);
+            n0 = dot4(t0[c], a0, n0);  d0 = dot4(a0, a0, d0);
+            n1 = dot4(t1[c], a1, n1);  d1 = dot4(a1, a1, d1);
+          }
+        }
+        n0 = group_sum<LP>(n0);  d0 = group_sum<LP>(d0);
+        n1 = group_sum<LP>(n1);  d1 = group_sum<LP>(d1);
+        if (gl == 0) {
+          if (c0 < D) nrm2[c0] = (d0 > 0.f) ? n0 / d0 : 0.f;
+          if (c1 < D) nrm2[c1] = (d1 > 0.f) ? n1 / d1 : 0.f;
         }
       }
-      num = group_sum<LP>(num);
-      den = group_sum<LP>(den);
-      if (col < D && gl == 0) nrm2[col] = (den > 0.f) ? num / den : 0.f;
+    } else {
+      for (int cb = 0; cb < D; cb += ngroups) {
+        const int col = cb + grp;
+        const float* u = U + (size_t)(col < D ? col : 0) * ld;
+        float4 tv[CH];
+        group_matvec<LP, CH>(Gk, u, D, ld, nch, gl, tv);
+        float num = 0.f, den = 0.f;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const int ch = gl + LP * c;
+          if (ch < nch) {
+            const float4 uv = *reinterpret_cast<const float4*>(u + 4 * ch);
+            num = dot4(tv[c], uv, num);
+            den = dot4(uv, uv, den);
+          }
+        }
+        num = group_sum<LP>(num);
+        den = group_sum<LP>(den);
+        if (col < D && gl == 0) nrm2[col] = (den > 0.f) ? num / den : 0.f;
+      }
     }
     __syncthreads();
     for (int i = tid; i < D; i += nthreads) wv[i] = nrm2[i];
@@ -566,7 +640,7 @@ int launch_eig_small(const EigArgs& a_in, int B, cudaStream_t st) {
     return nbuf * mat + extra <= 227 * 1024;
   };
   // padded columns (branch-free chunk loops) when that does not cost the second buffer
-  const int ld_pad = lp * chT * 4;
+  const int ld_pad = lp * chT * 4 + 4;   // +4: consecutive columns start 4 banks apart (no conflicts on scalar loads)
   const bool want2 = fits(a.ld, 2);
   bool pad = g_tune_pad != 0 && chT <= 4 && fits(ld_pad, want2 ? 2 : 1);
   if (pad) a.ld = ld_pad;

@@ -166,6 +166,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
+  // prefetch) may overlap the tail of the previous kernel in the stream; its results are only
+  // touched below this point.  The next kernel in the chain may begin its own prologue at once.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int tiles_per_batch = p.tiles_m * p.tiles_n;
   const int total_tiles = tiles_per_batch * p.batch;
@@ -389,8 +394,10 @@ void tc_forget_maps() {
 }
 
 static int g_num_sms = 0;
-static int g_tc_bn = 0;  // 0 = auto
+static int g_tc_bn = 0;   // 0 = auto
+static int g_tc_pdl = 1;  // programmatic dependent launch between the chained products
 int tc_tune_bn(int bn) { g_tc_bn = bn; return 0; }
+int tc_tune_pdl(int on) { g_tc_pdl = on; return 0; }
 
 template <int BN>
 static int launch_tc(const TcGemm& g, int batch, cudaStream_t st) {
@@ -420,7 +427,17 @@ static int launch_tc(const TcGemm& g, int batch, cudaStream_t st) {
   }
   const int grid = (int)(total < g_num_sms ? total : g_num_sms);
   profile_begin(st, 1, 2.0 * g.M * g.N * g.K * batch);
-  tc_gemm_kernel<BN><<<grid, tc::THREADS, C::SMEM, st>>>(mAh, mAl, mBh, mBl, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(tc::THREADS);
+  cfg.dynamicSmemBytes = C::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_tc_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  UGLAD_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN>, mAh, mAl, mBh, mBl, p));
   profile_end(st);
   UGLAD_CHECK_LAUNCH("tc_gemm_kernel");
   return 0;

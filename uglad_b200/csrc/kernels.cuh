@@ -82,6 +82,7 @@ struct TcGemm {
 bool tc_gemm_supported(const TcGemm& g);
 int launch_tc_gemm(const TcGemm& g, int batch, cudaStream_t st);
 int tc_tune_bn(int bn);
+int tc_tune_pdl(int on);
 void tc_forget_maps();
 
 // ---- large-D path: Newton-Schulz in GEMM form (ns_large.cu), blocked Cholesky (chol_large.cu)

@@ -17,12 +17,12 @@ def get_optimizers(model_glad: nn.Module, lr_glad: float = 0.002, use_optimizer:
 
 
 def glad(Sb: Tensor, model, lambda_init: float = 1, L: int = 15, INIT_DIAG: int = 0,
-         USE_CUDA: bool = True, exact_sqrt: bool = False, group=None) -> Tensor:
+         USE_CUDA: bool = True, exact_sqrt: bool = False, group=None, total_graphs=None) -> Tensor:
     """Sb [B,D,D] (or [D,D]) covariance -> theta_pred [B,D,D].  Same arguments as the
     reference; two extras: `exact_sqrt` replaces the reference's 10-step Newton-Schulz square
     root by the exact one, `group` is a torch.distributed process group when the batch is
-    sharded by graph over GPUs."""
+    sharded by graph over GPUs (`total_graphs`: the graph count over all ranks, if known)."""
     if Sb.dim() == 2:
         Sb = Sb.reshape(1, Sb.shape[0], Sb.shape[1])
     return ops.GladFunction.apply(Sb, model.packed(), int(L), int(INIT_DIAG), int(model.H),
-                                  float(lambda_init), bool(exact_sqrt), group)
+                                  float(lambda_init), bool(exact_sqrt), group, total_graphs)

@@ -31,11 +31,11 @@ def init_uGLAD(lr: float, theta_init_offset: float = 1.0, nF: int = 3, H: int = 
 
 
 def loss_uGLAD(theta: torch.Tensor, S: torch.Tensor, struct_theta: Optional[torch.Tensor] = None,
-               group=None) -> torch.Tensor:
+               group=None, total_graphs: Optional[int] = None) -> torch.Tensor:
     """main.py:289-335: sum_b(-logdet theta_b + <S_b, theta_b>) / B with B = S.shape[0]
     (the number of graphs over all processes when `group` shards them), plus the optional
     log-cosh structure prior."""
-    B = ops.global_graph_count(S.shape[0], S.device, group)
+    B = int(total_graphs) if total_graphs is not None else ops.global_graph_count(S.shape[0], S.device, group)
     loss = ops.GlassoLossFunction.apply(theta, S, float(B))
     if struct_theta is not None:
         D = S.shape[-1]
@@ -45,10 +45,13 @@ def loss_uGLAD(theta: torch.Tensor, S: torch.Tensor, struct_theta: Optional[torc
 
 
 def forward_uGLAD(Sb, model_glad, L: int = 15, INIT_DIAG: int = 0, loss_Sb=None, struct_theta=None,
-                  group=None):
-    """main.py:252-286: theta = glad(Sb); loss = glasso(theta, loss_Sb or Sb)."""
-    predTheta = glad.glad(Sb, model_glad, L=L, INIT_DIAG=INIT_DIAG, group=group)
-    loss = loss_uGLAD(predTheta, Sb if loss_Sb is None else loss_Sb, struct_theta=struct_theta, group=group)
+                  group=None, total_graphs: Optional[int] = None):
+    """main.py:252-286: theta = glad(Sb); loss = glasso(theta, loss_Sb or Sb).  With `group` the
+    graphs are sharded over ranks; `total_graphs` (their count over all ranks) saves the count
+    all-reduce of every call when the caller already knows it."""
+    predTheta = glad.glad(Sb, model_glad, L=L, INIT_DIAG=INIT_DIAG, group=group, total_graphs=total_graphs)
+    loss = loss_uGLAD(predTheta, Sb if loss_Sb is None else loss_Sb, struct_theta=struct_theta, group=group,
+                      total_graphs=total_graphs)
     return predTheta, loss
 
 
@@ -59,10 +62,11 @@ def _fit_loop(Sb, model, optimizer, EPOCHS, L, INIT_DIAG, VERBOSE, loss_Sb=None,
     to the host when it is printed (or when the NaN guard of the direct mode needs it)."""
     every = max(int(EPOCHS / 10), 1)
     predTheta, losses = None, []
+    total = ops.global_graph_count(Sb.shape[0], Sb.device, group) if group is not None else None
     for e in range(EPOCHS):
         optimizer.zero_grad()
         predTheta, loss = forward_uGLAD(Sb, model, L=L, INIT_DIAG=INIT_DIAG, loss_Sb=loss_Sb,
-                                        struct_theta=struct_theta, group=group)
+                                        struct_theta=struct_theta, group=group, total_graphs=total)
         if stop_on_nan and bool(torch.isnan(loss)):
             print(f"Warning: NaN loss encountered at epoch {e}. Try updating the parameters and train.")
             break

@@ -159,7 +159,7 @@ class GladFunction(torch.autograd.Function):
     """theta_pred = glad(S; params)  (glad.py:74-150) with the hand-written backward."""
 
     @staticmethod
-    def forward(ctx, S, flat_params, L, init_diag, H, lambda_init, exact_sqrt, group):
+    def forward(ctx, S, flat_params, L, init_diag, H, lambda_init, exact_sqrt, group, total_graphs=None):
         lib = _lib.load()
         S = _f32c(S, "Sb")
         flat_params = _f32c(flat_params, "params")
@@ -168,7 +168,8 @@ class GladFunction(torch.autograd.Function):
         if group is not None:
             import torch.distributed as dist
             world = dist.get_world_size(group)
-        B_total = global_graph_count(B, S.device, group)
+        # `total_graphs` (when the caller knows it) avoids an all-reduce + host sync per forward
+        B_total = int(total_graphs) if total_graphs is not None else global_graph_count(B, S.device, group)
         dims = make_dims(B, D, L, H, init_diag, B_total, exact_sqrt, lambda_init)
         if flat_params.numel() != lib.uglad_param_count(H):
             raise _lib.UgladError("packed parameter vector has the wrong length")
@@ -215,7 +216,7 @@ class GladFunction(torch.autograd.Function):
                                       _ptr(ctx.ws), _ptr(g), _ptr(gp), _stream(g)), "uglad_glad_backward")
         if ctx.world > 1:
             allreduce_shared_gradients(gp, ctx.group)
-        return None, gp, None, None, None, None, None, None
+        return None, gp, None, None, None, None, None, None, None
 
 
 class GlassoLossFunction(torch.autograd.Function):
