@@ -127,6 +127,15 @@ int uglad_profile_read(int kind, double* total_ms, unsigned long long* launches,
  * "tc_bn" (tile width of the tcgen05 kernel: 0 auto / 64 / 112 / 128).                      */
 int uglad_tune(const char* key, int value);
 
+/* developer timeline of the tcgen05 GEMM: buf = device int64[148][8] (NULL switches it off); each
+ * CTA stamps clock64 at {start, setup done, dependency wait done, first operands landed, last MMA
+ * committed, accumulator visible to the epilogue, epilogue done} for its first tile.          */
+int uglad_tc_debug_buffer(void* buf);
+/* developer benchmark: split the operands once, then `reps` back-to-back launches of the product
+ * (split_out: write the hi/lo pair into scratch instead of C).                                */
+int uglad_tc_gemm_repeat(const float* A, const float* B, float* C, int M, int N, int K, int batch, int reps,
+                         int split_out, float* scratch, void* stream);
+
 /* building blocks exported for the parity tests */
 /* the tcgen05 3xTF32 product of the large-D path on plain operands:
  * C[b] = alpha A[b] B[b]^T + beta E1[b] + diag I, A [batch][M][K], B [batch][N][K], C / E1 [batch][M][N]

@@ -43,6 +43,8 @@ SIGNATURES = {
     "uglad_profile": (_I, [_I, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),
     "uglad_profile_read": (_I, [_I, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong), C.POINTER(C.c_double)]),
     "uglad_tune": (_I, [C.c_char_p, _I]),
+    "uglad_tc_debug_buffer": (_I, [_P]),
+    "uglad_tc_gemm_repeat": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "uglad_tc_gemm_scratch_floats": (_Z, [_I, _I, _I, _I]),
     "uglad_tc_gemm": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P, _P]),
     "uglad_z_update": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),

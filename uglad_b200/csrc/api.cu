@@ -535,6 +535,12 @@ int uglad_tune(const char* key, int value) {
   return eig_small_tune(key, value);
 }
 
+int uglad_tc_gemm_repeat(const float* A, const float* Bm, float* C, int M, int N, int K, int batch, int reps,
+                         int split_out, float* scratch, void* stream) {
+  return tc_gemm_repeat(A, Bm, C, M, N, K, batch, reps, split_out, scratch, (cudaStream_t)stream);
+}
+int uglad_tc_debug_buffer(void* buf) { tc_set_debug(reinterpret_cast<long long*>(buf)); return 0; }
+
 size_t uglad_tc_gemm_scratch_floats(int M, int N, int K, int batch) { return tc_gemm_plain_scratch_floats(M, N, K, batch); }
 int uglad_tc_gemm(const float* A, const float* Bm, const float* E1, float* C, int M, int N, int K, int batch,
                   float alpha, float beta, float diag, float* scratch, void* stream) {

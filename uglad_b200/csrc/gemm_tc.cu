@@ -119,6 +119,7 @@ struct Cfg {
 }  // namespace tc
 
 struct TcParams {
+  long long* dbg;   // developer timeline: [grid][8] clock64 stamps (null = off)
   int M, N, K, batch, tiles_m, tiles_n;
   float alpha, beta, diag;
   const float* alpha_dev;
@@ -151,6 +152,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * C::STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 8 : nullptr;
+  if (dbg && threadIdx.x == 0) {
+    dbg[0] = clock64();
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    dbg[7] = (long long)gt;   // wall-clock (ns) of this CTA's start
+  }
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmAh); tc::tma_prefetch_desc(&tmAl);
     tc::tma_prefetch_desc(&tmBh); tc::tma_prefetch_desc(&tmBl);
@@ -169,8 +177,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
   // prefetch) may overlap the tail of the previous kernel in the stream; its results are only
   // touched below this point.  The next kernel in the chain may begin its own prologue at once.
+  if (dbg && threadIdx.x == 0) dbg[1] = clock64();
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (dbg && threadIdx.x == 0) dbg[2] = clock64();
 
   const int tiles_per_batch = p.tiles_m * p.tiles_n;
   const int total_tiles = tiles_per_batch * p.batch;
@@ -206,6 +216,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         for (int kb = 0; kb < num_kb; ++kb) {
           tc::mbar_wait(full_bar(stage), phase);
           tc::tc_fence_after();
+          if (dbg && kb == 0 && tile == (int)blockIdx.x) dbg[3] = clock64();
           const uint32_t sa = base + stage * C::STAGE_BYTES;
           const uint64_t dAh = tc::umma_desc(sa), dAl = tc::umma_desc(sa + tc::A_BYTES);
           const uint64_t dBh = tc::umma_desc(sa + 2 * tc::A_BYTES), dBl = tc::umma_desc(sa + 2 * tc::A_BYTES + C::B_BYTES);
@@ -221,6 +232,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
         tc::umma_commit(tfull_bar(acc));
+        if (dbg && tile == (int)blockIdx.x) dbg[4] = clock64();
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -237,6 +249,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       const int tm = r / p.tiles_n, tn = r - tm * p.tiles_n;
       tc::mbar_wait(tfull_bar(acc), acc_phase);
       tc::tc_fence_after();
+      if (dbg && tile == (int)blockIdx.x && warp == 2 && lane == 0) dbg[5] = clock64();
       const int row = tm * tc::BM + q * 32 + lane;
       const float alpha = p.alpha_dev ? p.alpha * p.alpha_dev[b] : p.alpha;
       float* Ch = p.C_hi + (size_t)b * p.sC + (size_t)row * p.ldc;
@@ -312,6 +325,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       }
       tc::tc_fence_before();
       __syncwarp();
+      if (dbg && tile == (int)blockIdx.x && warp == 2 && lane == 0) dbg[6] = clock64();
       if (lane == 0) tc::mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
@@ -319,6 +333,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 
   tc::tc_fence_before();
   __syncthreads();
+  if (dbg && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    dbg[0] = (long long)gt;   // wall-clock (ns) of this CTA's end (overwrites the cycle stamp)
+  }
   if (warp == 2) {
     tc::tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
@@ -398,6 +417,8 @@ static int g_tc_bn = 0;   // 0 = auto
 static int g_tc_pdl = 1;  // programmatic dependent launch between the chained products
 int tc_tune_bn(int bn) { g_tc_bn = bn; return 0; }
 int tc_tune_pdl(int on) { g_tc_pdl = on; return 0; }
+static long long* g_tc_dbg = nullptr;   // developer timeline buffer (uglad_tc_debug_buffer)
+void tc_set_debug(long long* buf) { g_tc_dbg = buf; }
 
 template <int BN>
 static int launch_tc(const TcGemm& g, int batch, cudaStream_t st) {
@@ -413,6 +434,7 @@ static int launch_tc(const TcGemm& g, int batch, cudaStream_t st) {
   if (get_map(g.B_hi, g.N, g.K, g.ldb, batch, g.sB, BN, &mBh)) return 1;
   if (get_map(g.B_lo, g.N, g.K, g.ldb, batch, g.sB, BN, &mBl)) return 1;
   TcParams p;
+  p.dbg = g_tc_dbg;
   p.M = g.M; p.N = g.N; p.K = g.K; p.batch = batch;
   p.tiles_m = (g.M + tc::BM - 1) / tc::BM;
   p.tiles_n = (g.N + BN - 1) / BN;

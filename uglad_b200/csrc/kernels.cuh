@@ -83,6 +83,7 @@ bool tc_gemm_supported(const TcGemm& g);
 int launch_tc_gemm(const TcGemm& g, int batch, cudaStream_t st);
 int tc_tune_bn(int bn);
 int tc_tune_pdl(int on);
+void tc_set_debug(long long* buf);
 void tc_forget_maps();
 
 // ---- large-D path: Newton-Schulz in GEMM form (ns_large.cu), blocked Cholesky (chol_large.cu)
@@ -106,6 +107,8 @@ int launch_tcs_split(const float* src, long long sSrc, int B, int rows, int cols
 int tc_gemm_plain(const float* A, const float* Bm, const float* E1, float* C, int M, int N, int K, int batch,
                   float alpha, float beta, float diag, float* scratch, cudaStream_t st);
 size_t tc_gemm_plain_scratch_floats(int M, int N, int K, int batch);
+int tc_gemm_repeat(const float* A, const float* Bm, float* C, int M, int N, int K, int batch, int reps,
+                   int split_out, float* scratch, cudaStream_t st);
 size_t chol_scratch_floats(int B, int D);
 int chol_factor(float* A, int B, int D, float shift, const float* shift_dev, float* logdet, float* scratch,
                 cudaStream_t st);

@@ -5,7 +5,8 @@
 // symmetric (a polynomial in b, or A / Q / H + H^T of the backward), or antisymmetric
 // (W = A Q - Q A, where the sign flips), so no transposes are ever materialised:
 //   forward   A = b b ; Y1 = (A/n) T0 ; { T = (3I - Z Y)/2 ; Y <- Y T ; Z <- T Z } ; X = (sqrt(n) Y T - b)/2
-//   backward  B3 = 3I - A A ; QB = Q B3 ; W = A Q - Q A ; Q <- (QB - A W)/2 = (QB + A W^T)/2 ; A <- A B3 / 2
+//   backward  B3 = 3I - A A ; QB = Q B3 ; P = A Q, W = P - P^T (= A Q - Q A) ; Q <- (QB - A W)/2 = (QB + A W^T)/2 ;
+//             A <- A B3 / 2      (5 products per iteration)
 #include "kernels.cuh"
 
 namespace uglad {
@@ -198,6 +199,39 @@ __global__ void tcs_hsym_kernel(const float* __restrict__ Qh, const float* __res
   }
 }
 
+// W = P - P^T in place on a split matrix (P = A Q with A, Q symmetric, so P^T = Q A): one block per
+// pair of mirrored 32x32 tiles, block (32, 8).
+__global__ void tcs_antisym_kernel(float* __restrict__ Ph, float* __restrict__ Pl, int D, int ldp) {
+  if (blockIdx.x > blockIdx.y) return;
+  __shared__ float ta[32][33], tb[32][33];
+  const size_t pbase = (size_t)blockIdx.z * D * ldp;
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int c = threadIdx.x;
+    const size_t oa = pbase + (size_t)(bx + r) * ldp + by + c;   // tile (bx, by)
+    const size_t ob = pbase + (size_t)(by + r) * ldp + bx + c;   // tile (by, bx)
+    ta[r][c] = (bx + r < D && by + c < D) ? Ph[oa] + Pl[oa] : 0.f;
+    tb[r][c] = (by + r < D && bx + c < D) ? Ph[ob] + Pl[ob] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int c = threadIdx.x;
+    float h, l;
+    if (bx + r < D && by + c < D) {
+      const size_t oa = pbase + (size_t)(bx + r) * ldp + by + c;
+      split_tf32(ta[r][c] - tb[c][r], h, l);
+      Ph[oa] = h;
+      Pl[oa] = l;
+    }
+    if (blockIdx.x != blockIdx.y && by + r < D && bx + c < D) {
+      const size_t ob = pbase + (size_t)(by + r) * ldp + bx + c;
+      split_tf32(tb[r][c] - ta[c][r], h, l);
+      Ph[ob] = h;
+      Pl[ob] = l;
+    }
+  }
+}
+
 // plain [B][rows][cols] (row stride ld, batch stride sSrc) -> split [B][rows][ldp]; optional transpose-free
 __global__ void __launch_bounds__(TCS_THREADS) tcs_split_kernel(const float* __restrict__ src, long long sSrc, int rows,
                                                                int cols, int ld, int ldp, float* __restrict__ hi,
@@ -325,8 +359,13 @@ int ns_tc_theta_update_backward(const float* S, long long sS, const float* Theta
   for (int t = 0; t < UGLAD_NS_ITERS; ++t) {
     { TMM m; m.A = A; m.Bm = A; m.C = B3; m.alpha = -1.f; m.diag = 3.f; if (tmm(m, s, B, D, st)) return 1; }
     { TMM m; m.A = Q; m.Bm = B3; m.C = QB; if (tmm(m, s, B, D, st)) return 1; }
-    { TMM m; m.A = Q; m.Bm = A; m.C = W; if (tmm(m, s, B, D, st)) return 1; }
-    { TMM m; m.A = A; m.Bm = Q; m.C = W; m.beta = -1.f; m.E1 = W; if (tmm(m, s, B, D, st)) return 1; }
+    { TMM m; m.A = A; m.Bm = Q; m.C = W; if (tmm(m, s, B, D, st)) return 1; }   // P = A Q
+    {                                                                            // W = P - P^T = A Q - Q A
+      const int nt = (D + 31) / 32;
+      dim3 g2(nt, nt, B), blk(32, 8);
+      tcs_antisym_kernel<<<g2, blk, 0, st>>>(W.hi, W.lo, D, s.ldp);
+      UGLAD_CHECK_LAUNCH("tcs_antisym_kernel");
+    }
     { TMM m; m.A = A; m.Bm = W; m.C = Q2; m.alpha = 0.5f; m.beta = 0.5f; m.E1 = QB; if (tmm(m, s, B, D, st)) return 1; }
     if (t + 1 < UGLAD_NS_ITERS) {
       TMM m; m.A = A; m.Bm = B3; m.C = A2; m.alpha = 0.5f;
@@ -365,9 +404,30 @@ int tc_gemm_plain(const float* A, const float* Bm, const float* E1, float* C, in
   g.C_hi = C; g.ldc = N; g.sC = (long long)M * N;
   return launch_tc_gemm(g, batch, st);
 }
-size_t tc_gemm_plain_scratch_floats(int M, int N, int K, int batch) {
-  const int ldk = (K + 3) & ~3;
-  return 2 * al4t((size_t)batch * M * ldk) + 2 * al4t((size_t)batch * N * ldk);
+// developer benchmark: split once, then `reps` back-to-back launches of the same product
+int tc_gemm_repeat(const float* A, const float* Bm, float* C, int M, int N, int K, int batch, int reps,
+                   int split_out, float* scratch, cudaStream_t st) {
+  const int ldk = (K + 3) & ~3, ldn = (N + 3) & ~3;
+  const size_t na = al4t((size_t)batch * M * ldk), nb = al4t((size_t)batch * N * ldk);
+  float *Ah = scratch, *Al = Ah + na, *Bh = Al + na, *Bl = Bh + nb;
+  float* Cs = Bl + nb;   // split output region: 2 * batch * M * ldn
+  if (launch_tcs_split(A, (long long)M * K, batch, M, K, K, ldk, Ah, Al, st)) return 1;
+  if (launch_tcs_split(Bm, (long long)N * K, batch, N, K, K, ldk, Bh, Bl, st)) return 1;
+  TcGemm g;
+  g.A_hi = Ah; g.A_lo = Al; g.B_hi = Bh; g.B_lo = Bl;
+  g.M = M; g.N = N; g.K = K; g.lda = g.ldb = ldk;
+  g.sA = (long long)M * ldk; g.sB = (long long)N * ldk;
+  if (split_out) {
+    g.C_hi = Cs; g.C_lo = Cs + al4t((size_t)batch * M * ldn); g.ldc = ldn; g.sC = (long long)M * ldn;
+  } else {
+    g.C_hi = C; g.ldc = N; g.sC = (long long)M * N;
+  }
+  for (int r = 0; r < reps; ++r)
+    if (launch_tc_gemm(g, batch, st)) return 1;
+  return 0;
 }
-
+size_t tc_gemm_plain_scratch_floats(int M, int N, int K, int batch) {
+  const int ldk0 = (K + 3) & ~3, ldn0 = (N + 3) & ~3;
+  return 2 * al4t((size_t)batch * M * ldk0) + 2 * al4t((size_t)batch * N * ldk0) + 2 * al4t((size_t)batch * M * ldn0);
+}
 }  // namespace uglad
