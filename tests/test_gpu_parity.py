@@ -432,3 +432,42 @@ def test_d1000_against_reference_golden(dev, path):
     assert abs(loss.item() - float(g["loss0"])) < 1e-4 * max(1.0, abs(float(g["loss0"])))
     for k, p in model.named_parameters():
         assert rel(p.grad.cpu().numpy(), g["g0/" + k]) < 1e-3, k
+
+
+# ---- callers either side of the hot path (DESIGN.md row f) ---------------------------------------
+def test_fit_api_missing_mode_consensus(dev):
+    """uGLAD_GL.fit(mode='missing') (main.py:553-644): mean imputation, K row-subsampled covariances
+    trained jointly against the full-data covariance, consensus by majority sign / min magnitude."""
+    from uglad_b200 import main as ug
+    from uglad_b200.utils import prepare_data
+    rng = np.random.default_rng(11)
+    Xb, _ = prepare_data.get_data(12, [0.2, 0.2], 240, batch_size=1, eig_offset=1.0, rng=rng)
+    Xm = prepare_data.add_noise_dropout(Xb, dropout=0.2, rng=rng)[0]
+    m = ug.uGLAD_GL()
+    m.fit(Xm, epochs=4, lr=0.002, L=15, verbose=False, mode="missing", k_fold=3)
+    assert m.precision_.shape == (12, 12) and np.isfinite(m.precision_).all()
+    assert np.allclose(m.precision_, m.precision_.T, atol=1e-5)
+
+
+def test_fit_api_cv_mode(dev):
+    """uGLAD_GL.fit(mode='cv') (main.py:428-550): per fold, keep the parameters with the best held-out loss."""
+    from uglad_b200 import main as ug
+    from uglad_b200.utils import prepare_data
+    rng = np.random.default_rng(12)
+    Xb, theta = prepare_data.get_data(10, [0.2, 0.2], 200, batch_size=1, eig_offset=1.0, rng=rng)
+    m = ug.uGLAD_GL()
+    res = m.fit(Xb[0], true_theta=theta[0], epochs=3, lr=0.002, L=15, verbose=False, mode="cv", k_fold=2)
+    assert m.precision_.shape == (10, 10) and np.isfinite(m.precision_).all()
+    assert isinstance(res, dict) and "auc" in {k.lower() for k in res}
+
+
+def test_multitask_api_ragged_sample_counts(dev):
+    """uGLAD_multitask.fit (main.py:155-226): one shared model, graphs with different sample counts."""
+    from uglad_b200 import main as ug
+    from uglad_b200.utils import prepare_data
+    rng = np.random.default_rng(13)
+    Xs = [prepare_data.get_data(9, [0.2, 0.2], m, batch_size=1, eig_offset=1.0, rng=rng)[0][0] for m in (120, 150, 120)]
+    mt = ug.uGLAD_multitask()
+    mt.fit(Xs, epochs=3, lr=0.002, L=15, verbose=False)
+    assert mt.precision_.shape == (3, 9, 9) and np.isfinite(mt.precision_).all()
+    assert mt.covariance_.shape == (3, 9, 9)
