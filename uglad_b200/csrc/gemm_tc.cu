@@ -118,9 +118,7 @@ struct Cfg {
 
 }  // namespace tc
 
-struct TcParams {
-  long long* dbg;   // developer timeline: [grid][8] clock64 stamps (null = off)
-  int M, N, K, batch, tiles_m, tiles_n;
+struct TcEpi {
   float alpha, beta, diag;
   const float* alpha_dev;
   const float* E1_hi;
@@ -132,11 +130,19 @@ struct TcParams {
   long long sC;
   int ldc;
 };
+struct TcParams {
+  long long* dbg;   // developer timeline: [grid][8] clock64 stamps (null = off)
+  int M, N, K, batch, tiles_m, tiles_n;
+  int nprob;        // 1, or 2: two independent products of the same shape share one launch
+  TcEpi e[2];
+};
 
 template <int BN>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
-               const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, TcParams p) {
+               const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+               const __grid_constant__ CUtensorMap tm2Ah, const __grid_constant__ CUtensorMap tm2Al,
+               const __grid_constant__ CUtensorMap tm2Bh, const __grid_constant__ CUtensorMap tm2Bl, TcParams p) {
   using C = tc::Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = tc::smem_u32(smem_raw);
@@ -162,6 +168,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tmAh); tc::tma_prefetch_desc(&tmAl);
     tc::tma_prefetch_desc(&tmBh); tc::tma_prefetch_desc(&tmBl);
+    if (p.nprob > 1) {
+      tc::tma_prefetch_desc(&tm2Ah); tc::tma_prefetch_desc(&tm2Al);
+      tc::tma_prefetch_desc(&tm2Bh); tc::tma_prefetch_desc(&tm2Bl);
+    }
     for (int s = 0; s < C::STAGES; ++s) { tc::mbar_init(full_bar(s), 1); tc::mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { tc::mbar_init(tfull_bar(a), 1); tc::mbar_init(tempty_bar(a), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -182,7 +192,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (dbg && threadIdx.x == 0) dbg[2] = clock64();
 
-  const int tiles_per_batch = p.tiles_m * p.tiles_n;
+  // tile index -> (graph b, problem, tile row, tile column); the two problems of a dual launch
+  // alternate inside a graph so that neighbouring CTAs keep sharing operand rows in L2
+  const int tiles_per_prob = p.tiles_m * p.tiles_n;
+  const int tiles_per_batch = tiles_per_prob * p.nprob;
   const int total_tiles = tiles_per_batch * p.batch;
   const int num_kb = (p.K + tc::BK - 1) / tc::BK;
 
@@ -190,16 +203,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int b = tile / tiles_per_batch, r = tile - b * tiles_per_batch;
+        const int b = tile / tiles_per_batch, r0 = tile - b * tiles_per_batch;
+        const int prob = r0 / tiles_per_prob, r = r0 - prob * tiles_per_prob;
         const int tm = r / p.tiles_n, tn = r - tm * p.tiles_n;
+        const CUtensorMap* mAh = prob ? &tm2Ah : &tmAh;
+        const CUtensorMap* mAl = prob ? &tm2Al : &tmAl;
+        const CUtensorMap* mBh = prob ? &tm2Bh : &tmBh;
+        const CUtensorMap* mBl = prob ? &tm2Bl : &tmBl;
         for (int kb = 0; kb < num_kb; ++kb) {
           tc::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = base + stage * C::STAGE_BYTES;
           tc::mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
-          tc::tma_load_3d(sa, &tmAh, full_bar(stage), kb * tc::BK, tm * tc::BM, b);
-          tc::tma_load_3d(sa + tc::A_BYTES, &tmAl, full_bar(stage), kb * tc::BK, tm * tc::BM, b);
-          tc::tma_load_3d(sa + 2 * tc::A_BYTES, &tmBh, full_bar(stage), kb * tc::BK, tn * BN, b);
-          tc::tma_load_3d(sa + 2 * tc::A_BYTES + C::B_BYTES, &tmBl, full_bar(stage), kb * tc::BK, tn * BN, b);
+          tc::tma_load_3d(sa, mAh, full_bar(stage), kb * tc::BK, tm * tc::BM, b);
+          tc::tma_load_3d(sa + tc::A_BYTES, mAl, full_bar(stage), kb * tc::BK, tm * tc::BM, b);
+          tc::tma_load_3d(sa + 2 * tc::A_BYTES, mBh, full_bar(stage), kb * tc::BK, tn * BN, b);
+          tc::tma_load_3d(sa + 2 * tc::A_BYTES + C::B_BYTES, mBl, full_bar(stage), kb * tc::BK, tn * BN, b);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -240,22 +258,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   } else {
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     int acc = 0; uint32_t acc_phase = 0;
-    const bool vec_c = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C_hi) & 15) == 0) &&
-                       (p.C_lo == nullptr || (reinterpret_cast<uintptr_t>(p.C_lo) & 15) == 0) && (p.sC % 4 == 0);
-    const bool vec_e = p.E1_hi != nullptr && (p.lde1 % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.E1_hi) & 15) == 0) &&
-                       (p.E1_lo == nullptr || (reinterpret_cast<uintptr_t>(p.E1_lo) & 15) == 0) && (p.sE1 % 4 == 0);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int b = tile / tiles_per_batch, r = tile - b * tiles_per_batch;
+      const int b = tile / tiles_per_batch, r0 = tile - b * tiles_per_batch;
+      const int prob = r0 / tiles_per_prob, r = r0 - prob * tiles_per_prob;
       const int tm = r / p.tiles_n, tn = r - tm * p.tiles_n;
+      const TcEpi& ep = p.e[prob];
+      const bool vec_c = (ep.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.C_hi) & 15) == 0) &&
+                         (ep.C_lo == nullptr || (reinterpret_cast<uintptr_t>(ep.C_lo) & 15) == 0) && (ep.sC % 4 == 0);
+      const bool vec_e = ep.E1_hi != nullptr && (ep.lde1 % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.E1_hi) & 15) == 0) &&
+                         (ep.E1_lo == nullptr || (reinterpret_cast<uintptr_t>(ep.E1_lo) & 15) == 0) && (ep.sE1 % 4 == 0);
       tc::mbar_wait(tfull_bar(acc), acc_phase);
       tc::tc_fence_after();
       if (dbg && tile == (int)blockIdx.x && warp == 2 && lane == 0) dbg[5] = clock64();
       const int row = tm * tc::BM + q * 32 + lane;
-      const float alpha = p.alpha_dev ? p.alpha * p.alpha_dev[b] : p.alpha;
-      float* Ch = p.C_hi + (size_t)b * p.sC + (size_t)row * p.ldc;
-      float* Cl = p.C_lo ? p.C_lo + (size_t)b * p.sC + (size_t)row * p.ldc : nullptr;
-      const float* Eh = p.E1_hi ? p.E1_hi + (size_t)b * p.sE1 + (size_t)row * p.lde1 : nullptr;
-      const float* El = p.E1_lo ? p.E1_lo + (size_t)b * p.sE1 + (size_t)row * p.lde1 : nullptr;
+      const float alpha = ep.alpha_dev ? ep.alpha * ep.alpha_dev[b] : ep.alpha;
+      const float beta = ep.beta, diag = ep.diag;
+      float* Ch = ep.C_hi + (size_t)b * ep.sC + (size_t)row * ep.ldc;
+      float* Cl = ep.C_lo ? ep.C_lo + (size_t)b * ep.sC + (size_t)row * ep.ldc : nullptr;
+      const float* Eh = ep.E1_hi ? ep.E1_hi + (size_t)b * ep.sE1 + (size_t)row * ep.lde1 : nullptr;
+      const float* El = ep.E1_lo ? ep.E1_lo + (size_t)b * ep.sE1 + (size_t)row * ep.lde1 : nullptr;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
@@ -272,12 +293,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             if (Eh) {
               if (full4 && vec_e) {
                 const float4 eh = *reinterpret_cast<const float4*>(Eh + col);
-                o[0] = fmaf(p.beta, eh.x, o[0]); o[1] = fmaf(p.beta, eh.y, o[1]);
-                o[2] = fmaf(p.beta, eh.z, o[2]); o[3] = fmaf(p.beta, eh.w, o[3]);
+                o[0] = fmaf(beta, eh.x, o[0]); o[1] = fmaf(beta, eh.y, o[1]);
+                o[2] = fmaf(beta, eh.z, o[2]); o[3] = fmaf(beta, eh.w, o[3]);
                 if (El) {
                   const float4 el = *reinterpret_cast<const float4*>(El + col);
-                  o[0] = fmaf(p.beta, el.x, o[0]); o[1] = fmaf(p.beta, el.y, o[1]);
-                  o[2] = fmaf(p.beta, el.z, o[2]); o[3] = fmaf(p.beta, el.w, o[3]);
+                  o[0] = fmaf(beta, el.x, o[0]); o[1] = fmaf(beta, el.y, o[1]);
+                  o[2] = fmaf(beta, el.z, o[2]); o[3] = fmaf(beta, el.w, o[3]);
                 }
               } else {
 #pragma unroll
@@ -285,14 +306,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                   if (col + e < p.N) {
                     float ev = Eh[col + e];
                     if (El) ev += El[col + e];
-                    o[e] = fmaf(p.beta, ev, o[e]);
+                    o[e] = fmaf(beta, ev, o[e]);
                   }
               }
             }
-            if (p.diag != 0.f) {
+            if (diag != 0.f) {
 #pragma unroll
               for (int e = 0; e < 4; ++e)
-                if (col + e == row) o[e] += p.diag;
+                if (col + e == row) o[e] += diag;
             }
             if (Cl) {
               float h[4], l[4];
@@ -417,38 +438,51 @@ static int g_tc_bn = 0;   // 0 = auto
 static int g_tc_pdl = 1;  // programmatic dependent launch between the chained products
 int tc_tune_bn(int bn) { g_tc_bn = bn; return 0; }
 int tc_tune_pdl(int on) { g_tc_pdl = on; return 0; }
+static int g_tc_dual = 1;  // pair independent same-shape products into one launch
+int tc_tune_dual(int on) { g_tc_dual = on; return 0; }
 static long long* g_tc_dbg = nullptr;   // developer timeline buffer (uglad_tc_debug_buffer)
 void tc_set_debug(long long* buf) { g_tc_dbg = buf; }
 
+static void fill_epi(TcEpi& e, const TcGemm& g) {
+  e.alpha = g.alpha; e.beta = g.beta; e.diag = g.diag; e.alpha_dev = g.alpha_dev;
+  e.E1_hi = g.E1_hi; e.E1_lo = g.E1_lo; e.sE1 = g.sE1; e.lde1 = g.lde1;
+  e.C_hi = g.C_hi; e.C_lo = g.C_lo; e.sC = g.sC; e.ldc = g.ldc;
+}
+
+// g2 == nullptr: one product; otherwise two independent products of identical shape in one launch
 template <int BN>
-static int launch_tc(const TcGemm& g, int batch, cudaStream_t st) {
+static int launch_tc(const TcGemm& g, const TcGemm* g2, int batch, cudaStream_t st) {
   using C = tc::Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
     UGLAD_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     attr_set = true;
   }
-  CUtensorMap mAh, mAl, mBh, mBl;
-  if (get_map(g.A_hi, g.M, g.K, g.lda, batch, g.sA, tc::BM, &mAh)) return 1;
-  if (get_map(g.A_lo, g.M, g.K, g.lda, batch, g.sA, tc::BM, &mAl)) return 1;
-  if (get_map(g.B_hi, g.N, g.K, g.ldb, batch, g.sB, BN, &mBh)) return 1;
-  if (get_map(g.B_lo, g.N, g.K, g.ldb, batch, g.sB, BN, &mBl)) return 1;
+  CUtensorMap m[8];
+  const TcGemm* gs[2] = {&g, g2 ? g2 : &g};
+  for (int i = 0; i < 2; ++i) {
+    const TcGemm& q = *gs[i];
+    if (get_map(q.A_hi, q.M, q.K, q.lda, batch, q.sA, tc::BM, &m[4 * i + 0])) return 1;
+    if (get_map(q.A_lo, q.M, q.K, q.lda, batch, q.sA, tc::BM, &m[4 * i + 1])) return 1;
+    if (get_map(q.B_hi, q.N, q.K, q.ldb, batch, q.sB, BN, &m[4 * i + 2])) return 1;
+    if (get_map(q.B_lo, q.N, q.K, q.ldb, batch, q.sB, BN, &m[4 * i + 3])) return 1;
+  }
   TcParams p;
   p.dbg = g_tc_dbg;
   p.M = g.M; p.N = g.N; p.K = g.K; p.batch = batch;
   p.tiles_m = (g.M + tc::BM - 1) / tc::BM;
   p.tiles_n = (g.N + BN - 1) / BN;
-  p.alpha = g.alpha; p.beta = g.beta; p.diag = g.diag; p.alpha_dev = g.alpha_dev;
-  p.E1_hi = g.E1_hi; p.E1_lo = g.E1_lo; p.sE1 = g.sE1; p.lde1 = g.lde1;
-  p.C_hi = g.C_hi; p.C_lo = g.C_lo; p.sC = g.sC; p.ldc = g.ldc;
-  const long long total = (long long)p.tiles_m * p.tiles_n * batch;
+  p.nprob = g2 ? 2 : 1;
+  fill_epi(p.e[0], g);
+  fill_epi(p.e[1], *gs[1]);
+  const long long total = (long long)p.tiles_m * p.tiles_n * batch * p.nprob;
   if (g_num_sms == 0) {
     int dev = 0;
     UGLAD_CUDA(cudaGetDevice(&dev));
     UGLAD_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = (int)(total < g_num_sms ? total : g_num_sms);
-  profile_begin(st, 1, 2.0 * g.M * g.N * g.K * batch);
+  profile_begin(st, 1, 2.0 * g.M * g.N * g.K * batch * p.nprob);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(tc::THREADS);
@@ -459,7 +493,7 @@ static int launch_tc(const TcGemm& g, int batch, cudaStream_t st) {
   attr[0].val.programmaticStreamSerializationAllowed = g_tc_pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  UGLAD_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN>, mAh, mAl, mBh, mBl, p));
+  UGLAD_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN>, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], p));
   profile_end(st);
   UGLAD_CHECK_LAUNCH("tc_gemm_kernel");
   return 0;
@@ -471,14 +505,19 @@ bool tc_gemm_supported(const TcGemm& g) {
          al16(g.B_hi) && al16(g.B_lo) && g.M > 0 && g.N > 0 && g.K > 0;
 }
 
-int launch_tc_gemm(const TcGemm& g, int batch, cudaStream_t st) {
-  if (!tc_gemm_supported(g)) { set_error("tc_gemm: operands must be 16-byte aligned with ld %% 4 == 0"); return 1; }
+static int launch_tc_any(const TcGemm& g, const TcGemm* g2, int batch, cudaStream_t st) {
+  if (!tc_gemm_supported(g) || (g2 && !tc_gemm_supported(*g2))) {
+    set_error("tc_gemm: operands must be 16-byte aligned with ld %% 4 == 0");
+    return 1;
+  }
+  if (g2 && (g2->M != g.M || g2->N != g.N || g2->K != g.K)) { set_error("tc_gemm: dual launch needs identical shapes"); return 1; }
   if (batch <= 0) return 0;
   if (g_num_sms == 0) {
     int dev = 0;
     UGLAD_CUDA(cudaGetDevice(&dev));
     UGLAD_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
+  const int nprob = g2 ? 2 : 1;
   int bn = g_tc_bn;
   if (bn == 0) {
     // narrowest tile that covers N in one pass; for wide N pick the width that fills the SMs best
@@ -490,20 +529,25 @@ int launch_tc_gemm(const TcGemm& g, int batch, cudaStream_t st) {
       double best = 1e300;
       const int cand[3] = {128, 112, 64};
       for (int c : cand) {
-        const long long tiles = tm * ((g.N + c - 1) / c) * batch;
+        const long long tiles = tm * ((g.N + c - 1) / c) * batch * nprob;
         const long long waves = (tiles + g_num_sms - 1) / g_num_sms;
-        const double cost = (double)waves * (c + 40);   // MMA time ~ BN, fixed per-tile overhead
+        const double cost = (double)waves * (c + 40);   // per-tile time ~ operand rows, fixed overhead
         if (cost < best) { best = cost; bn = c; }
       }
     }
   }
   switch (bn) {
-    case 64: return launch_tc<64>(g, batch, st);
-    case 112: return launch_tc<112>(g, batch, st);
-    case 128: return launch_tc<128>(g, batch, st);
+    case 64: return launch_tc<64>(g, g2, batch, st);
+    case 112: return launch_tc<112>(g, g2, batch, st);
+    case 128: return launch_tc<128>(g, g2, batch, st);
   }
   set_error("tc_gemm: unsupported tile width %d", bn);
   return 1;
+}
+int launch_tc_gemm(const TcGemm& g, int batch, cudaStream_t st) { return launch_tc_any(g, nullptr, batch, st); }
+int launch_tc_gemm2(const TcGemm& g1, const TcGemm& g2, int batch, cudaStream_t st) {
+  return g_tc_dual ? launch_tc_any(g1, &g2, batch, st)
+                   : (launch_tc_any(g1, nullptr, batch, st) || launch_tc_any(g2, nullptr, batch, st));
 }
 
 }  // namespace uglad

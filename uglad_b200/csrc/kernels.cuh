@@ -81,6 +81,9 @@ struct TcGemm {
 };
 bool tc_gemm_supported(const TcGemm& g);
 int launch_tc_gemm(const TcGemm& g, int batch, cudaStream_t st);
+// two independent products of identical shape in ONE launch (twice the tiles for the persistent grid)
+int launch_tc_gemm2(const TcGemm& g1, const TcGemm& g2, int batch, cudaStream_t st);
+int tc_tune_dual(int on);
 int tc_tune_bn(int bn);
 int tc_tune_pdl(int on);
 void tc_set_debug(long long* buf);

@@ -179,6 +179,7 @@ int ns_tune(const char* key, int value) {
   if (!strcmp(key, "use_tc")) { g_use_tc = value ? 1 : 0; return 0; }
   if (!strcmp(key, "tc_bn")) return tc_tune_bn(value);
   if (!strcmp(key, "tc_pdl")) return tc_tune_pdl(value);
+  if (!strcmp(key, "tc_dual")) return tc_tune_dual(value);
   return 1;
 }
 

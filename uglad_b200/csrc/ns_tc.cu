@@ -300,7 +300,7 @@ struct TMM {
   float diag = 0.f;
   int ldc = 0; long long sC = 0;
 };
-static int tmm(const TMM& m, const TcsBuf& s, int B, int D, cudaStream_t st) {
+static TcGemm to_gemm(const TMM& m, const TcsBuf& s, int D) {
   TcGemm g;
   g.A_hi = m.A.hi; g.A_lo = m.A.lo; g.B_hi = m.Bm.hi; g.B_lo = m.Bm.lo;
   g.M = g.N = g.K = D;
@@ -313,7 +313,14 @@ static int tmm(const TMM& m, const TcsBuf& s, int B, int D, cudaStream_t st) {
   g.C_hi = m.C.hi; g.C_lo = m.C.lo;
   g.ldc = m.ldc ? m.ldc : s.ldp;
   g.sC = m.sC ? m.sC : (long long)D * s.ldp;
-  return launch_tc_gemm(g, B, st);
+  return g;
+}
+static int tmm(const TMM& m, const TcsBuf& s, int B, int D, cudaStream_t st) {
+  return launch_tc_gemm(to_gemm(m, s, D), B, st);
+}
+// two products that do not depend on each other: one launch
+static int tmm2(const TMM& m1, const TMM& m2, const TcsBuf& s, int B, int D, cudaStream_t st) {
+  return launch_tc_gemm2(to_gemm(m1, s, D), to_gemm(m2, s, D), B, st);
 }
 
 int ns_tc_theta_update_forward(const float* S, long long sS, const float* Theta, const float* lam, int B, int D,
@@ -332,8 +339,11 @@ int ns_tc_theta_update_forward(const float* S, long long sS, const float* Theta,
   for (int t = 1; t < UGLAD_NS_ITERS; ++t) {
     { TMM m; m.A = Z; m.Bm = Y; m.C = T; m.alpha = -0.5f; m.diag = 1.5f; if (tmm(m, s, B, D, st)) return 1; }
     if (t + 1 < UGLAD_NS_ITERS) {
-      { TMM m; m.A = Y; m.Bm = T; m.C = Y2; if (tmm(m, s, B, D, st)) return 1; }
-      { TMM m; m.A = T; m.Bm = Z; m.C = Z2; if (tmm(m, s, B, D, st)) return 1; }
+      {
+        TMM m1; m1.A = Y; m1.Bm = T; m1.C = Y2;
+        TMM m2; m2.A = T; m2.Bm = Z; m2.C = Z2;
+        if (tmm2(m1, m2, s, B, D, st)) return 1;
+      }
       SplitMat tmp = Y; Y = Y2; Y2 = tmp;
       tmp = Z; Z = Z2; Z2 = tmp;
     } else {
@@ -357,21 +367,25 @@ int ns_tc_theta_update_backward(const float* S, long long sS, const float* Theta
   tcs_scale_aq_kernel<<<grid, TCS_THREADS, 0, st>>>(A.hi, A.lo, GX, s.scal, B, D, s.ldp, Q.hi, Q.lo);
   UGLAD_CHECK_LAUNCH("tcs_scale_aq_kernel");
   for (int t = 0; t < UGLAD_NS_ITERS; ++t) {
-    { TMM m; m.A = A; m.Bm = A; m.C = B3; m.alpha = -1.f; m.diag = 3.f; if (tmm(m, s, B, D, st)) return 1; }
-    { TMM m; m.A = Q; m.Bm = B3; m.C = QB; if (tmm(m, s, B, D, st)) return 1; }
-    { TMM m; m.A = A; m.Bm = Q; m.C = W; if (tmm(m, s, B, D, st)) return 1; }   // P = A Q
-    {                                                                            // W = P - P^T = A Q - Q A
+    {  // B3 = 3I - A A  and  P = A Q  (independent)
+      TMM m1; m1.A = A; m1.Bm = A; m1.C = B3; m1.alpha = -1.f; m1.diag = 3.f;
+      TMM m2; m2.A = A; m2.Bm = Q; m2.C = W;
+      if (tmm2(m1, m2, s, B, D, st)) return 1;
+    }
+    {  // W = P - P^T = A Q - Q A
       const int nt = (D + 31) / 32;
       dim3 g2(nt, nt, B), blk(32, 8);
       tcs_antisym_kernel<<<g2, blk, 0, st>>>(W.hi, W.lo, D, s.ldp);
       UGLAD_CHECK_LAUNCH("tcs_antisym_kernel");
     }
-    { TMM m; m.A = A; m.Bm = W; m.C = Q2; m.alpha = 0.5f; m.beta = 0.5f; m.E1 = QB; if (tmm(m, s, B, D, st)) return 1; }
-    if (t + 1 < UGLAD_NS_ITERS) {
-      TMM m; m.A = A; m.Bm = B3; m.C = A2; m.alpha = 0.5f;
-      if (tmm(m, s, B, D, st)) return 1;
-      SplitMat tmp = A; A = A2; A2 = tmp;
+    const bool last = t + 1 == UGLAD_NS_ITERS;
+    {  // QB = Q B3  and  A' = A B3 / 2  (independent; A' is not needed after the last iteration)
+      TMM m1; m1.A = Q; m1.Bm = B3; m1.C = QB;
+      TMM m2; m2.A = A; m2.Bm = B3; m2.C = A2; m2.alpha = 0.5f;
+      if (last ? tmm(m1, s, B, D, st) : tmm2(m1, m2, s, B, D, st)) return 1;
     }
+    { TMM m; m.A = A; m.Bm = W; m.C = Q2; m.alpha = 0.5f; m.beta = 0.5f; m.E1 = QB; if (tmm(m, s, B, D, st)) return 1; }
+    if (!last) { SplitMat tmp = A; A = A2; A2 = tmp; }
     SplitMat tmp = Q; Q = Q2; Q2 = tmp;
   }
   {
