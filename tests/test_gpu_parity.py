@@ -471,3 +471,19 @@ def test_multitask_api_ragged_sample_counts(dev):
     mt.fit(Xs, epochs=3, lr=0.002, L=15, verbose=False)
     assert mt.precision_.shape == (3, 9, 9) and np.isfinite(mt.precision_).all()
     assert mt.covariance_.shape == (3, 9, 9)
+
+
+def test_covariance_prefetcher_matches_direct_path(dev):
+    """The side-stream input pipeline returns exactly what get_covariance returns."""
+    from uglad_b200.utils import prepare_data
+    rng = np.random.default_rng(14)
+    Xs = [torch.from_numpy(rng.random((3, 80, 11)).astype(np.float32)).pin_memory() for _ in range(3)]
+    pf = prepare_data.CovariancePrefetcher(dev)
+    pf.submit(Xs[0])
+    for i in range(3):
+        S = pf.get()
+        if i + 1 < 3:
+            pf.submit(Xs[i + 1])
+        torch.cuda.synchronize()
+        ref = prepare_data.get_covariance(Xs[i].to(dev))
+        assert torch.equal(S, ref)

@@ -50,6 +50,40 @@ def get_covariance(Xb, offset: float = 0.1) -> torch.Tensor:
     return out
 
 
+class CovariancePrefetcher:
+    """Input pipeline for repeated fits on fresh sample batches: the host->device copy of the NEXT
+    batch and its covariance + conditioning run on a side stream while the current batch trains.
+
+        pf = CovariancePrefetcher(); pf.submit(X0_pinned)
+        for each step:  S = pf.get(); loss = step(S); pf.submit(X_next_pinned); loss.item()
+
+    Contract: the tensors are allocated on the side stream's pool, so the consumer must have
+    synchronised the work that reads S (reading the step's loss does) before S is dropped; the
+    prefetcher additionally keeps the two most recent batches referenced."""
+
+    def __init__(self, device=None, offset: float = 0.1):
+        self.device = _device() if device is None else device
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.offset = offset
+        self._pending = None
+        self._keep = []
+
+    def submit(self, X_host: torch.Tensor) -> None:
+        with torch.cuda.stream(self.stream):
+            Xd = X_host.to(self.device, non_blocking=True)
+            S = get_covariance(Xd, offset=self.offset)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self._pending = (S, ev, Xd)
+
+    def get(self) -> torch.Tensor:
+        S, ev, Xd = self._pending
+        self._pending = None
+        torch.cuda.current_stream(self.device).wait_event(ev)
+        self._keep = (self._keep + [(S, Xd)])[-2:]
+        return S
+
+
 # ---- host-side table hygiene (prepare_data.py:361-516 with its default arguments) ---------
 def normalize_table(df, typeN: str):
     if typeN == "min_max":
