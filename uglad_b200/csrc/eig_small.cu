@@ -66,6 +66,12 @@ __device__ __forceinline__ float group_sum_masked(float v, unsigned mask) {
   return v;
 }
 
+// MUFU approximations without the denormal fix-up sequences of the library wrappers: the rotation
+// angle only steers the convergence (Jacobi corrects any O(ulp) error in the next sweep)
+__device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 __device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
 }
@@ -325,16 +331,16 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
         const float g2s = ga * ga;
         // |cos(u_p, u_q)| > tol  <=>  ga^2 > tol^2 |u_p|^2 |u_q|^2  (no rsqrt on the common path)
         if (valid && g2s > tol2 * den) {
-          wmax = fmaxf(wmax, g2s / den);
+          wmax = 1.f;   // only "did anything rotate" is consumed
           const float d = be - al, g2 = 2.f * ga;
-          const float h = sqrtf(fmaf(d, d, g2 * g2));
-          float t = __fdividef(fabsf(g2), fabsf(d) + h);
+          const float h = fast_sqrt(fmaf(d, d, g2 * g2));
+          float t = fabsf(g2) * fast_rcp(fabsf(d) + h);
           t = ((d < 0.f) != (g2 < 0.f)) ? -t : t;
           const float x = fmaf(t, t, 1.f);
-          float cs = rsqrtf(x);
+          float cs = fast_rsqrt(x);
           cs = cs * fmaf(-0.5f * x, cs * cs, 1.5f);  // one Newton step: ~0.5 ulp
           const float sn = t * cs;
-          const float tau = __fdividef(sn, 1.f + cs);
+          const float tau = sn * fast_rcp(1.f + cs);
 #pragma unroll
           for (int c = 0; c < CH; ++c) {
             if (PAD || gl + LP * c < nch) {
