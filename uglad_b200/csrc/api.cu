@@ -339,6 +339,7 @@ int uglad_glad_layer_forward(const uglad_dims* d, int k, const float* S, const f
   a.f = fk; a.sroot = ws + w.sroot + (size_t)k * w.n1; a.snorm = ws + w.snorm + (size_t)k * B;
   a.scratch = ws + w.eig_scratch;
   a.warmVt = warm_ws ? warm_ws + w.Vt + (size_t)k * w.n2 : nullptr;
+  a.warm_w = warm_ws ? warm_ws + w.beta + (size_t)k * w.n1 : nullptr;
   a.D = D; a.shift_mode = 1; a.tail = TAIL_LAYER; a.exact_sqrt = d->exact_sqrt;
   if (launch_eig(a, B, st)) return 1;
   if (ns_use_tc()) {  // X = (V diag f) V^T on the tensor pipe; the split eigenvectors are kept for the backward

@@ -191,7 +191,13 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
     trace = block_sum(trace_part, red);
     if (a.shift_mode == 1) {
       float bound;
-      if (attempt == 0) {
+      if (attempt == 0 && a.warm_w != nullptr && a.warmVt != nullptr) {
+        // warm start: the previous epoch's eigenvalues of the same layer ARE its spectral norm
+        // (the matrix moved by one optimiser step, far inside the 35 % margin)
+        float mx = 0.f;
+        for (int i = tid; i < D; i += nthreads) mx = fmaxf(mx, fabsf(a.warm_w[(size_t)b * D + i]));
+        bound = 1.35f * block_max(mx, red);
+      } else if (attempt == 0) {
         // power iteration on the symmetric U: ||A||_2 estimate (a lower bound, hence x1.35)
         for (int i = tid; i < ld; i += nthreads) {
           const unsigned h = (unsigned)(i + 1) * 2654435761u;

@@ -23,6 +23,7 @@ struct EigArgs {
   float* snorm = nullptr;        // TAIL_LAYER: [B] ||s||_2 ; TAIL_LOSS: [B] logdet
   float* scratch = nullptr;      // large-D path only
   const float* warmVt = nullptr; // optional [B][D][D] eigenvectors of a nearby matrix (warm start)
+  const float* warm_w = nullptr; // optional [B][D] eigenvalues of that matrix (replaces the norm estimate)
   int keepG = 0;                 // set by the launcher: second shared-memory buffer holds A + sigma I
   int D = 0, ld = 0, build = 0, shift_mode = 1, tail = TAIL_PLAIN, exact_sqrt = 0;
   int max_sweeps = 40;
