@@ -129,6 +129,59 @@ __device__ __forceinline__ void group_matvec2(const float* __restrict__ G, const
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// G * [8 columns] on the warp-level tensor path (mma.sync m16n8k8 TF32, 3xTF32 split in registers):
+// the D^3 products of the solver (warm start U0 = G V_prev, Rayleigh quotients) are the only
+// GEMM-shaped work of this kernel; as SIMT matvecs they were shared-memory-bandwidth bound.
+//   A[m][k] = G[m][k] from shared memory (G is symmetric, so the column-major copy serves),
+//   B[k][n] = Bsrc[(c0 + n) * ldb + k]   (shared or global memory), n = 0..7,
+//   acc[rt][0..3] = rows 16*(tile0 + rt) + {g, g, g + 8, g + 8}, columns c0 + {2t, 2t + 1, 2t, 2t + 1}.
+__device__ __forceinline__ void split2(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+constexpr int MMA_RT = 4;  // row tiles (of 16) accumulated per pass: 16 accumulator registers
+__device__ __forceinline__ void mma_g_times_cols(const float* __restrict__ G, int ld, int D,
+                                                 const float* __restrict__ Bsrc, int ldb, int c0, int tile0,
+                                                 int lane, float (*acc)[4]) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int rt = 0; rt < MMA_RT; ++rt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[rt][e] = 0.f;
+  const int col = c0 + g;
+  const bool colok = col < D;
+  const float* bp = Bsrc + (size_t)(colok ? col : 0) * ldb;
+  for (int k0 = 0; k0 < D; k0 += 8) {
+    const int ka = k0 + t, kb = ka + 4;
+    const float bx0 = (colok && ka < D) ? bp[ka] : 0.f;
+    const float bx1 = (colok && kb < D) ? bp[kb] : 0.f;
+    uint32_t bh0, bl0, bh1, bl1;
+    split2(bx0, bh0, bl0);
+    split2(bx1, bh1, bl1);
+#pragma unroll
+    for (int rt = 0; rt < MMA_RT; ++rt) {
+      const int m0 = (tile0 + rt) * 16 + g, m1 = m0 + 8;
+      if ((tile0 + rt) * 16 >= D) break;   // warp-uniform
+      const float ax0 = (m0 < D && ka < D) ? G[(size_t)m0 * ld + ka] : 0.f;
+      const float ax1 = (m1 < D && ka < D) ? G[(size_t)m1 * ld + ka] : 0.f;
+      const float ax2 = (m0 < D && kb < D) ? G[(size_t)m0 * ld + kb] : 0.f;
+      const float ax3 = (m1 < D && kb < D) ? G[(size_t)m1 * ld + kb] : 0.f;
+      uint32_t ah0, al0, ah1, al1, ah2, al2, ah3, al3;
+      split2(ax0, ah0, al0); split2(ax1, ah1, al1); split2(ax2, ah2, al2); split2(ax3, ah3, al3);
+      mma_tf32(acc[rt], al0, al1, al2, al3, bh0, bh1);
+      mma_tf32(acc[rt], ah0, ah1, ah2, ah3, bl0, bl1);
+      mma_tf32(acc[rt], ah0, ah1, ah2, ah3, bh0, bh1);
+    }
+  }
+}
+
 constexpr int eig_max_threads(int LP, int CH) {
   const int want = (116 * LP + 31) / 32 * 32, cap = (CH >= 8) ? 512 : 1024;  // CH=8 needs >64 registers
   return want > cap ? cap : want;
@@ -244,6 +297,34 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
       if (a.warmVt != nullptr && attempt == 0) {
         // U_0 = G V_prev, column by column in place: U[:,k] = V_prev[k][:] then U[:,k] <- G U[:,k]
         const float* Vp = a.warmVt + base;
+        if (a.use_mma) {
+          // tensor path: B fragments straight from global V_prev, the product lands in U
+          for (int idx = tid; idx < D * ld; idx += nthreads) {   // zero the padding rows of U
+            const int row = idx % ld;
+            if (row >= D) U[idx] = 0.f;
+          }
+          const int ntile = (D + 15) / 16;
+          for (int cg = warp; cg * 8 < D; cg += nwarps) {
+            for (int tile0 = 0; tile0 < ntile; tile0 += MMA_RT) {
+              float acc[MMA_RT][4];
+              mma_g_times_cols(Gk, ld, D, Vp, D, cg * 8, tile0, lane, acc);
+              const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+              for (int rt = 0; rt < MMA_RT; ++rt) {
+                const int m0 = (tile0 + rt) * 16 + g, m1 = m0 + 8;
+                const int cA = cg * 8 + 2 * t, cB = cA + 1;
+                if (cA < D) {
+                  if (m0 < D) U[(size_t)cA * ld + m0] = acc[rt][0];
+                  if (m1 < D) U[(size_t)cA * ld + m1] = acc[rt][2];
+                }
+                if (cB < D) {
+                  if (m0 < D) U[(size_t)cB * ld + m0] = acc[rt][1];
+                  if (m1 < D) U[(size_t)cB * ld + m1] = acc[rt][3];
+                }
+              }
+            }
+          }
+        } else {
         for (int idx = tid; idx < D * ld; idx += nthreads) {
           const int col = idx / ld, row = idx - col * ld;
           U[idx] = (row < D) ? Vp[(size_t)col * D + row] : 0.f;
@@ -282,6 +363,7 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
             }
           }
         }
+        }  // !use_mma
       } else {
         for (int idx = tid; idx < D * ld; idx += nthreads) U[idx] = Gk[idx];
       }
@@ -480,7 +562,43 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
   __syncthreads();
   if (a.keepG) {
     // Rayleigh quotients with the kept G = A + sigma I: lambda_k = u^T G u / u^T u - sigma
-    if constexpr (CH <= 4) {
+    if (a.use_mma) {
+      const int ntile = (D + 15) / 16;
+      const int g = lane >> 2, t = lane & 3;
+      for (int cg = warp; cg * 8 < D; cg += nwarps) {
+        const int cA = cg * 8 + 2 * t, cB = cA + 1;
+        const float* uA = U + (size_t)(cA < D ? cA : 0) * ld;
+        const float* uB = U + (size_t)(cB < D ? cB : 0) * ld;
+        float nA = 0.f, dA = 0.f, nB = 0.f, dB = 0.f;
+        for (int tile0 = 0; tile0 < ntile; tile0 += MMA_RT) {
+          float acc[MMA_RT][4];
+          mma_g_times_cols(Gk, ld, D, U, ld, cg * 8, tile0, lane, acc);
+#pragma unroll
+          for (int rt = 0; rt < MMA_RT; ++rt) {
+            const int m0 = (tile0 + rt) * 16 + g, m1 = m0 + 8;
+            if (m0 < D) {
+              const float a0 = uA[m0], b0 = uB[m0];
+              nA = fmaf(acc[rt][0], a0, nA); dA = fmaf(a0, a0, dA);
+              nB = fmaf(acc[rt][1], b0, nB); dB = fmaf(b0, b0, dB);
+            }
+            if (m1 < D) {
+              const float a1 = uA[m1], b1 = uB[m1];
+              nA = fmaf(acc[rt][2], a1, nA); dA = fmaf(a1, a1, dA);
+              nB = fmaf(acc[rt][3], b1, nB); dB = fmaf(b1, b1, dB);
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {   // reduce over the 8 row groups g (lanes with equal t)
+          nA += __shfl_xor_sync(0xffffffffu, nA, o); dA += __shfl_xor_sync(0xffffffffu, dA, o);
+          nB += __shfl_xor_sync(0xffffffffu, nB, o); dB += __shfl_xor_sync(0xffffffffu, dB, o);
+        }
+        if (g == 0) {
+          if (cA < D) nrm2[cA] = (dA > 0.f) ? nA / dA : 0.f;
+          if (cB < D) nrm2[cB] = (dB > 0.f) ? nB / dB : 0.f;
+        }
+      }
+    } else if constexpr (CH <= 4) {
       for (int cb = 0; cb < D; cb += 2 * ngroups) {
         const int c0 = cb + 2 * grp, c1 = c0 + 1;
         const float* u0 = U + (size_t)(c0 < D ? c0 : 0) * ld;
@@ -603,12 +721,14 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
 static int g_tune_lp = 0;      // 0 = auto; otherwise force lanes per column pair (4/8/16/32)
 static int g_tune_keepg = -1;  // -1 = auto (keep G when two buffers fit); 0 / 1 force
 static int g_tune_timing = 0;
+static int g_tune_mma = 1;     // 1 = warm-start product and Rayleigh quotients on the mma.sync tensor path
 static int g_tune_pad = 1;     // 1 = pad shared-memory columns to LP*CH*4 floats when it fits
 int eig_small_tune(const char* key, int value) {
   if (!strcmp(key, "eig_lp")) { g_tune_lp = value; return 0; }
   if (!strcmp(key, "eig_keepg")) { g_tune_keepg = value; return 0; }
   if (!strcmp(key, "eig_pad")) { g_tune_pad = value; return 0; }
   if (!strcmp(key, "eig_timing")) { g_tune_timing = value; return 0; }
+  if (!strcmp(key, "eig_mma")) { g_tune_mma = value; return 0; }
   return 1;
 }
 
@@ -631,6 +751,7 @@ static int launch_cfg(const EigArgs& a, int B, size_t smem, cudaStream_t st) {
 int launch_eig_small(const EigArgs& a_in, int B, cudaStream_t st) {
   EigArgs a = a_in;
   a.timing = g_tune_timing;
+  a.use_mma = g_tune_mma;
   a.ld = (a.D + 3) & ~3;
   if (a.D > UGLAD_SMALL_D_MAX) {
     set_error("eig_small: D=%d exceeds the shared-memory solver limit %d", a.D, UGLAD_SMALL_D_MAX);

@@ -27,6 +27,7 @@ struct EigArgs {
   int keepG = 0;                 // set by the launcher: second shared-memory buffer holds A + sigma I
   int D = 0, ld = 0, build = 0, shift_mode = 1, tail = TAIL_PLAIN, exact_sqrt = 0;
   int max_sweeps = 40;
+  int use_mma = 1;               // warm-start product / Rayleigh quotients via mma.sync (3xTF32)
   int timing = 0;                // developer knob: info[1..3] <- phase cycle counts
   float tol = 1e-6f;
 };
