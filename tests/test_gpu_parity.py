@@ -487,3 +487,55 @@ def test_covariance_prefetcher_matches_direct_path(dev):
         torch.cuda.synchronize()
         ref = prepare_data.get_covariance(Xs[i].to(dev))
         assert torch.equal(S, ref)
+
+
+# ---- edge cases ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("D,B,L,idg", [(1, 2, 3, 0), (2, 1, 15, 0), (3, 5, 2, 1), (165, 1, 2, 0), (167, 2, 2, 0),
+                                       (167, 1, 2, 1), (10, 600, 3, 0)])
+def test_edge_shapes_match_oracle(dev, D, B, L, idg):
+    """Degenerate and boundary shapes: D = 1, tiny D, either side of the eigensolver / large-D
+    threshold (166), INIT_DIAG on the large-D path, more graphs than the grid has SMs."""
+    from uglad_b200 import main as ug, ops
+    from uglad_b200.glad.glad_params import GladParams
+    ops.reset_warm_start()
+    rng = np.random.default_rng(1000 * D + B)
+    X = rng.random((B, max(2 * D, 8), D))
+    S = torch.tensor(O.covariance(X), dtype=torch.float32)
+    P = O.init_params(D + B)
+    model = GladParams(1.0, 3, 3)
+    model.load_state_dict({k: v.detach() for k, v in P.items()})
+    th_o, loss_o = O.forward_loss(S, P, L, idg)
+    loss_o.backward()
+    th, loss = ug.forward_uGLAD(S.to(dev), model, L=L, INIT_DIAG=idg)
+    loss.backward()
+    assert rel(th.detach().cpu().numpy(), th_o.detach().numpy()) < THETA_TOL
+    assert abs(loss.item() - loss_o.item()) < 1e-4 * max(1.0, abs(loss_o.item()))
+    for k, p in model.named_parameters():
+        assert rel(p.grad.cpu().numpy(), P[k].grad.numpy()) < 2e-3, k
+
+
+def test_inputs_need_not_be_contiguous_float32(dev):
+    from uglad_b200 import main as ug, ops
+    g = np.load(os.path.join(ROOT, "tests", "golden", "d10_m500.npz"))
+    ops.reset_warm_start()
+    S64 = torch.tensor(g["S"], device=dev, dtype=torch.float64)
+    St = S64.transpose(1, 2)  # symmetric: same values, non-contiguous view
+    model = load_model(g, "p0")
+    with torch.no_grad():
+        th = ug.glad.glad(St, model, L=int(g["L"]), INIT_DIAG=int(g["init_diag"]))
+    assert rel(th.cpu().numpy(), g["theta0"]) < THETA_TOL
+
+
+def test_exact_sqrt_is_refused_on_the_large_path(dev):
+    from uglad_b200 import main as ug, _lib
+    S = torch.eye(170, device=dev)[None] * 0.5
+    model = ug.init_uGLAD(lr=0.002)[0]
+    with pytest.raises(_lib.UgladError):
+        ug.glad.glad(S, model, L=2, exact_sqrt=True)
+
+
+def test_cpu_tensors_are_refused(dev):
+    from uglad_b200 import main as ug, _lib
+    model = ug.init_uGLAD(lr=0.002)[0]
+    with pytest.raises(_lib.UgladError):
+        ug.glad.glad(torch.eye(4)[None], model, L=2)
