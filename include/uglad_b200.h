@@ -57,6 +57,15 @@ size_t uglad_eigh_scratch_floats(int B, int D);
 int uglad_eigh(const float* A, int B, int D, int shift_mode, float* w, float* Vt, float* info,
                float* scratch, void* stream);
 
+/* same with a warm start: warm_Vt / warm_w = eigenvectors / eigenvalues of a NEARBY matrix batch of
+ * the same shape (e.g. the previous batch of a stream of similar sample matrices).  They only
+ * change the work done (fewer Jacobi sweeps), never the converged result; NULL = cold.         */
+int uglad_eigh_warm(const float* A, int B, int D, int shift_mode, float* w, float* Vt, float* info,
+                    float* scratch, const float* warm_Vt, const float* warm_w, void* stream);
+int uglad_condition_covariance_warm(float* S, int B, int D, float offset, float* wS, float* VtS,
+                                    float* info, float* scratch, const float* warm_Vt, const float* warm_w,
+                                    void* stream);
+
 /* prepare_data.py:345-355: eigen-decompose S; if min eig <= 1e-6 add (offset - min) to the
  * diagonal of S (in place) and to wS.  wS / VtS are reused by every later forward.        */
 int uglad_condition_covariance(float* S, int B, int D, float offset, float* wS, float* VtS,

@@ -18,10 +18,12 @@ def step(S):
     loss.backward(); opt.step()
     return loss
 side = torch.cuda.Stream(device=dev)
+WARM = [None, False]
 def stage(record):
     with torch.cuda.stream(side):
         Xd = X_host.to(dev, non_blocking=True)
-        S = prepare_data.get_covariance(Xd)
+        S = prepare_data.get_covariance(Xd, warm=WARM[0] if WARM[1] else None)
+        WARM[0] = S
         ev = torch.cuda.Event(); ev.record(side)
     return S, ev, Xd
 def run(mode, n=12):
@@ -44,6 +46,20 @@ def run(mode, n=12):
             if mode == "pipe_sync":
                 side.synchronize()
             ts.append(time.perf_counter() - t0)
+            if ts[-1] > 0.03:
+                st = torch.cuda.memory_stats()
+                print(f"   spike it={i} {ts[-1]*1e3:.0f} ms: device_alloc {st['num_device_alloc']} device_free {st['num_device_free']} retries {st['num_alloc_retries']} reserved {st['reserved_bytes.all.current']/1e9:.2f} GB", flush=True)
             del S, Xd
     print(f"{wl} {mode}: per-iteration ms {[round(t*1e3,1) for t in ts]}  loss {l:.4f}", flush=True)
-run("seq"); run("pipe"); run("pipe_sync"); run("seq")
+import sys
+if len(sys.argv) > 2:
+    ops.tune("tc_pdl", int(sys.argv[2]))
+run("seq", 6)
+pf = prepare_data.CovariancePrefetcher(dev)
+pf.submit(X_host)
+ts = []
+for i in range(40):
+    t0 = time.perf_counter()
+    S = pf.get(); loss = step(S); pf.submit(X_host); l = float(loss.item())
+    ts.append(time.perf_counter() - t0)
+print("slots:", [round(t*1e3,1) for t in ts], l, "device_alloc", torch.cuda.memory_stats()['num_device_alloc'])

@@ -539,3 +539,19 @@ def test_cpu_tensors_are_refused(dev):
     model = ug.init_uGLAD(lr=0.002)[0]
     with pytest.raises(_lib.UgladError):
         ug.glad.glad(torch.eye(4)[None], model, L=2)
+
+
+def test_warm_started_conditioning_gives_the_same_covariance(dev):
+    """A warm start (eigenvectors of a similar earlier batch) only changes the work, not the result,
+    including when the rank-deficient repair triggers."""
+    from uglad_b200.utils import prepare_data
+    rng = np.random.default_rng(15)
+    X0 = rng.standard_normal((3, 6, 14))            # fewer samples than features: repair triggers
+    X1 = X0 + 1e-3 * rng.standard_normal(X0.shape)
+    S0 = prepare_data.get_covariance(X0)
+    cold = prepare_data.get_covariance(X1)
+    warm = prepare_data.get_covariance(X1, warm=S0)
+    assert rel(warm.cpu().numpy(), cold.cpu().numpy()) < 1e-6
+    assert rel(warm.cpu().numpy(), O.covariance(X1, offset=0.1)) < 1e-5
+    w_c, w_w = cold._uglad_eig[1].wS.cpu().numpy(), warm._uglad_eig[1].wS.cpu().numpy()
+    assert np.abs(np.sort(w_c, 1) - np.sort(w_w, 1)).max() < 1e-5

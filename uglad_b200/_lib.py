@@ -29,6 +29,8 @@ SIGNATURES = {
     "uglad_eigh_scratch_floats": (_Z, [_I, _I]),
     "uglad_eigh": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P]),
     "uglad_condition_covariance": (_I, [_P, _I, _I, _F, _P, _P, _P, _P, _P]),
+    "uglad_eigh_warm": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "uglad_condition_covariance_warm": (_I, [_P, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
     "uglad_condition_scratch_floats": (_Z, [_I, _I]),
     "uglad_small_d_max": (_I, []),
     "uglad_workspace_floats": (_Z, [_DP]),

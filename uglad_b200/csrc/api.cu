@@ -194,13 +194,18 @@ int uglad_covariance(const float* X, int B, int M, int D, float* S, float* mean_
 
 size_t uglad_eigh_scratch_floats(int B, int D) { return eig_scratch_floats(B, D); }
 
-int uglad_eigh(const float* A, int B, int D, int shift_mode, float* w, float* Vt, float* info,
-               float* scratch, void* stream) {
+int uglad_eigh_warm(const float* A, int B, int D, int shift_mode, float* w, float* Vt, float* info,
+                    float* scratch, const float* warm_Vt, const float* warm_w, void* stream) {
   if (!A || !w || !Vt || B <= 0 || D <= 0) { set_error("eigh: bad arguments"); return 1; }
   EigArgs a;
   a.A = A; a.w = w; a.Vt = Vt; a.info = info; a.scratch = scratch;
   a.D = D; a.shift_mode = shift_mode; a.tail = TAIL_PLAIN;
+  a.warmVt = warm_Vt; a.warm_w = warm_Vt ? warm_w : nullptr;
   return launch_eig(a, B, (cudaStream_t)stream);
+}
+int uglad_eigh(const float* A, int B, int D, int shift_mode, float* w, float* Vt, float* info,
+               float* scratch, void* stream) {
+  return uglad_eigh_warm(A, B, D, shift_mode, w, Vt, info, scratch, nullptr, nullptr, stream);
 }
 
 // prepare_data.py:345-355 for D > small_d_max(): "min eig <= 1e-6" is decided by a Cholesky
@@ -260,14 +265,19 @@ size_t uglad_condition_scratch_floats(int B, int D) {
   return al4((size_t)B * D * D) + al4(B) + al4(chol_scratch_floats(B, D));
 }
 
-int uglad_condition_covariance(float* S, int B, int D, float offset, float* wS, float* VtS,
-                               float* info, float* scratch, void* stream) {
+int uglad_condition_covariance_warm(float* S, int B, int D, float offset, float* wS, float* VtS,
+                                    float* info, float* scratch, const float* warm_Vt, const float* warm_w,
+                                    void* stream) {
   if (D > small_d_max()) {
     if (!S || !scratch || B <= 0) { set_error("condition_covariance: bad arguments"); return 1; }
     return condition_large(S, B, D, offset, scratch, (cudaStream_t)stream);
   }
-  if (uglad_eigh(S, B, D, 1, wS, VtS, info, scratch, stream)) return 1;
+  if (uglad_eigh_warm(S, B, D, 1, wS, VtS, info, scratch, warm_Vt, warm_w, stream)) return 1;
   return launch_condition(S, wS, B, D, offset, (cudaStream_t)stream);
+}
+int uglad_condition_covariance(float* S, int B, int D, float offset, float* wS, float* VtS,
+                               float* info, float* scratch, void* stream) {
+  return uglad_condition_covariance_warm(S, B, D, offset, wS, VtS, info, scratch, nullptr, nullptr, stream);
 }
 
 int uglad_small_d_max(void) { return small_d_max(); }

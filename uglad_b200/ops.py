@@ -60,7 +60,9 @@ class ConditionedCovariance:
     """S after the eigenvalue repair of prepare_data.py:345-355 plus its eigendecomposition,
     which every forward reuses for theta_0 = (S + t I)^-1 (glad.py:115-117)."""
 
-    def __init__(self, S: torch.Tensor, offset: float = 0.1, repair: bool = True):
+    def __init__(self, S: torch.Tensor, offset: float = 0.1, repair: bool = True, warm=None):
+        """`warm`: an earlier ConditionedCovariance of the same shape (e.g. the previous batch of a
+        stream of similar sample matrices); its eigenvectors seed the solver."""
         S = _f32c(S, "S").clone()
         B, D, _ = S.shape
         lib = _lib.load()
@@ -78,13 +80,16 @@ class ConditionedCovariance:
         self.info = torch.empty(B, 4, device=S.device, dtype=torch.float32)
         ns = lib.uglad_eigh_scratch_floats(B, D)
         scratch = torch.empty(max(ns, 1), device=S.device, dtype=torch.float32)
+        wV = ww = None
+        if warm is not None and warm.VtS is not None and warm.VtS.shape == self.VtS.shape:
+            wV, ww = warm.VtS, warm.wS
         if repair:
-            check(lib.uglad_condition_covariance(_ptr(S), B, D, float(offset), _ptr(self.wS), _ptr(self.VtS),
-                                                 _ptr(self.info), _ptr(scratch), _stream(S)),
+            check(lib.uglad_condition_covariance_warm(_ptr(S), B, D, float(offset), _ptr(self.wS), _ptr(self.VtS),
+                                                      _ptr(self.info), _ptr(scratch), _ptr(wV), _ptr(ww), _stream(S)),
                   "uglad_condition_covariance")
         else:
-            check(lib.uglad_eigh(_ptr(S), B, D, 1, _ptr(self.wS), _ptr(self.VtS), _ptr(self.info),
-                                 _ptr(scratch), _stream(S)), "uglad_eigh")
+            check(lib.uglad_eigh_warm(_ptr(S), B, D, 1, _ptr(self.wS), _ptr(self.VtS), _ptr(self.info),
+                                      _ptr(scratch), _ptr(wV), _ptr(ww), _stream(S)), "uglad_eigh")
 
 
 def _eig_of(S: torch.Tensor) -> ConditionedCovariance:

@@ -27,10 +27,11 @@ def convert_to_torch(data, req_grad: bool = False, use_cuda: bool = True) -> tor
     return data
 
 
-def get_covariance(Xb, offset: float = 0.1) -> torch.Tensor:
+def get_covariance(Xb, offset: float = 0.1, warm=None) -> torch.Tensor:
     """prepare_data.py:328-356.  Xb: [B,M,D] array/tensor or a list of [M_b,D] arrays with
     different sample counts (multitask mode).  Returns the conditioned covariances as a CUDA
-    tensor [B,D,D] with their eigendecomposition attached for glad()'s theta_0."""
+    tensor [B,D,D] with their eigendecomposition attached for glad()'s theta_0.  `warm`: the
+    result of an earlier call on similar data (same shapes); it seeds the eigensolver."""
     dev = _device()
     if torch.is_tensor(Xb) or (isinstance(Xb, np.ndarray) and Xb.ndim == 3):
         X = convert_to_torch(Xb)
@@ -44,43 +45,88 @@ def get_covariance(Xb, offset: float = 0.1) -> torch.Tensor:
         for shp, idx in shapes.items():
             X = torch.from_numpy(np.stack([mats[i] for i in idx])).to(dev)
             S[idx] = ops.covariance(X)
-    cc = ops.ConditionedCovariance(S, offset=offset, repair=True)
+    wcc = getattr(warm, "_uglad_eig", (None, None))[1] if warm is not None else None
+    cc = ops.ConditionedCovariance(S, offset=offset, repair=True, warm=wcc)
     out = cc.S
     out._uglad_eig = (out._version, cc)
     return out
 
 
 class CovariancePrefetcher:
-    """Input pipeline for repeated fits on fresh sample batches: the host->device copy of the NEXT
-    batch and its covariance + conditioning run on a side stream while the current batch trains.
+    """Input pipeline for repeated fits on fresh sample batches of one shape [B, M, D]: the
+    host->device copy of the NEXT batch and its covariance + conditioning run on a side stream while
+    the current batch trains.
 
         pf = CovariancePrefetcher(); pf.submit(X0_pinned)
         for each step:  S = pf.get(); loss = step(S); pf.submit(X_next_pinned); loss.item()
 
-    Contract: the tensors are allocated on the side stream's pool, so the consumer must have
-    synchronised the work that reads S (reading the step's loss does) before S is dropped; the
-    prefetcher additionally keeps the two most recent batches referenced."""
+    Everything is staged in three rotating, preallocated slots (no allocator traffic on the side
+    stream, which would otherwise synchronise the device now and then): the tensor returned by
+    get() is overwritten three submits later.  Consecutive batches seed each other's eigensolver
+    (a warm start changes the work, never the result)."""
+
+    SLOTS = 3
 
     def __init__(self, device=None, offset: float = 0.1):
         self.device = _device() if device is None else device
         self.stream = torch.cuda.Stream(device=self.device)
-        self.offset = offset
+        self.offset = float(offset)
+        self._slots = None
+        self._n = 0
         self._pending = None
-        self._keep = []
+
+    def _make_slots(self, shape):
+        import ctypes as C
+        from .. import _lib
+        lib = _lib.load()
+        B, M, D = shape
+        large = D > lib.uglad_small_d_max()
+        f = dict(device=self.device, dtype=torch.float32)
+        slots = []
+        for _ in range(self.SLOTS):
+            sl = {"X": torch.empty(B, M, D, **f), "S": torch.empty(B, D, D, **f), "mean": torch.empty(B, D, **f),
+                  "scratch": torch.empty(max(lib.uglad_condition_scratch_floats(B, D), 1), **f),
+                  "ev": torch.cuda.Event()}
+            cc = ops.ConditionedCovariance.__new__(ops.ConditionedCovariance)
+            cc.S = sl["S"]
+            if large:
+                cc.wS = cc.VtS = cc.info = None
+            else:
+                cc.wS, cc.VtS, cc.info = torch.empty(B, D, **f), torch.empty(B, D, D, **f), torch.empty(B, 4, **f)
+            sl["cc"] = cc
+            slots.append(sl)
+        return slots
 
     def submit(self, X_host: torch.Tensor) -> None:
+        import ctypes as C
+        from .. import _lib
+        lib = _lib.load()
+        if X_host.dim() == 2:
+            X_host = X_host.unsqueeze(0)
+        if self._slots is None or tuple(self._slots[0]["X"].shape) != tuple(X_host.shape):
+            self._slots, self._n = self._make_slots(tuple(X_host.shape)), 0
+        sl = self._slots[self._n % self.SLOTS]
+        prev = self._slots[(self._n - 1) % self.SLOTS]["cc"] if self._n > 0 else None
+        self._n += 1
+        B, M, D = sl["X"].shape
+        P = lambda t: C.c_void_p(0 if t is None else t.data_ptr())
         with torch.cuda.stream(self.stream):
-            Xd = X_host.to(self.device, non_blocking=True)
-            S = get_covariance(Xd, offset=self.offset)
-            ev = torch.cuda.Event()
-            ev.record(self.stream)
-        self._pending = (S, ev, Xd)
+            st = C.c_void_p(self.stream.cuda_stream)
+            sl["X"].copy_(X_host, non_blocking=True)
+            ops.check(lib.uglad_covariance(P(sl["X"]), B, M, D, P(sl["S"]), P(sl["mean"]), st), "uglad_covariance")
+            cc = sl["cc"]
+            wV, ww = (prev.VtS, prev.wS) if (prev is not None and prev.VtS is not None) else (None, None)
+            ops.check(lib.uglad_condition_covariance_warm(P(sl["S"]), B, D, self.offset, P(cc.wS), P(cc.VtS),
+                                                          P(cc.info), P(sl["scratch"]), P(wV), P(ww), st),
+                      "uglad_condition_covariance")
+            sl["ev"].record(self.stream)
+        self._pending = sl
 
     def get(self) -> torch.Tensor:
-        S, ev, Xd = self._pending
-        self._pending = None
-        torch.cuda.current_stream(self.device).wait_event(ev)
-        self._keep = (self._keep + [(S, Xd)])[-2:]
+        sl, self._pending = self._pending, None
+        torch.cuda.current_stream(self.device).wait_event(sl["ev"])
+        S = sl["S"]
+        S._uglad_eig = (S._version, sl["cc"])
         return S
 
 
