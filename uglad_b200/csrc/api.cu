@@ -147,6 +147,21 @@ static int tc_mm(const float* Ah, const float* Al, const float* Bh, const float*
   g.sC = Cl ? (long long)D * ldp : (long long)D * D;
   return launch_tc_gemm(g, B, st);
 }
+// C = alpha V diag(f) V^T + beta E1 on the tensor pipe: split / transpose the eigenvectors into
+// `sp` (6 * n2p floats: Vt, V, V diag f as hi/lo pairs), then one tcgen05 product
+static int spectral_recon_tc(const float* Vt, const float* f, float* C, int B, int D, int ldp, size_t n2p,
+                             float* sp, float alpha, const float* E1, long long sE1, float beta, cudaStream_t st) {
+  float *T = sp, *V = sp + 2 * n2p, *VF = sp + 4 * n2p;
+  if (launch_eigvec_split(Vt, f, B, D, ldp, T, T + n2p, V, V + n2p, VF, VF + n2p, st)) return 1;
+  TcGemm g;
+  g.A_hi = VF; g.A_lo = VF + n2p; g.B_hi = V; g.B_lo = V + n2p;
+  g.M = g.N = g.K = D;
+  g.lda = g.ldb = ldp;
+  g.sA = g.sB = (long long)D * ldp;
+  g.alpha = alpha; g.beta = beta; g.E1_hi = E1; g.sE1 = sE1; g.lde1 = D;
+  g.C_hi = C; g.ldc = D; g.sC = (long long)D * D;
+  return launch_tc_gemm(g, B, st);
+}
 static int bgemm(const float* A, int tA, const float* Bm, int tB, float* C, int B, int D, cudaStream_t st) {
   GemmArgs g;
   g.A = A; g.Bm = Bm; g.C = C;
@@ -320,6 +335,8 @@ int uglad_glad_init_forward(const uglad_dims* d, const float* S, const float* pa
   }
   if (!wS || !VtS) { set_error("glad_init_forward: INIT_DIAG=0 needs the eigen-decomposition of S"); return 1; }
   if (launch_init_f(wS, params, d->B, d->D, ws + w.f0, st)) return 1;
+  if (ns_use_tc())
+    return spectral_recon_tc(VtS, ws + w.f0, ws + w.theta, d->B, d->D, w.ldp, w.n2p, ws + w.sp, 1.f, nullptr, 0, 0.f, st);
   return spectral_recon(VtS, ws + w.f0, ws + w.theta, d->B, d->D, 1.f, nullptr, 0, st);
 }
 
@@ -443,7 +460,13 @@ int uglad_glad_backward(const uglad_dims* d, const float* S, const float* params
   if (d->init_diag == 1) {
     if (launch_dot_partial(G, ws + w.theta, B, D, 1, ws + w.t0_part, st)) return 1;
   } else {
-    if (bgemm(ws + w.theta, 0, ws + w.theta, 0, T1, B, D, st)) return 1;
+    if (!w.large && ns_use_tc()) {  // theta_0 is symmetric: theta_0 theta_0^T on the tensor pipe
+      float* Ts = ws + w.sp;
+      if (launch_tcs_split(ws + w.theta, (long long)D * D, B, D, D, D, w.ldp, Ts, Ts + w.n2p, st)) return 1;
+      if (tc_mm(Ts, Ts + w.n2p, Ts, Ts + w.n2p, T1, nullptr, B, D, w.ldp, st)) return 1;
+    } else if (bgemm(ws + w.theta, 0, ws + w.theta, 0, T1, B, D, st)) {
+      return 1;
+    }
     if (launch_dot_partial(G, T1, B, D, 0, ws + w.t0_part, st)) return 1;
   }
   return launch_finalize_grads(params, d->H, L, (int)w.nblk, ws + w.rho_part, ws + w.trh_part,
@@ -455,7 +478,8 @@ size_t uglad_loss_scratch_floats(int B, int D) {
   const size_t n2 = (size_t)B * D * D, n1 = (size_t)B * D;
   const size_t lp = al4((size_t)B * loss_blocks_per_graph(D));
   if (D > small_d_max()) return 2 * al4(n2) + 2 * al4(B) + 8 + lp + al4(chol_scratch_floats(B, D));
-  return al4(n2) + 2 * al4(n1) + 2 * al4(B) + al4(4 * (size_t)B) + 8 + lp + al4(eig_scratch_floats(B, D));
+  const size_t n2p = al4((size_t)B * D * ((D + 3) & ~3));
+  return al4(n2) + 2 * al4(n1) + 2 * al4(B) + al4(4 * (size_t)B) + 8 + lp + al4(eig_scratch_floats(B, D)) + 6 * n2p;
 }
 
 int uglad_glasso_loss(const float* theta, const float* S, int B, int D, int S_batch, float Bdiv,
@@ -498,6 +522,12 @@ int uglad_glasso_loss(const float* theta, const float* S, int B, int D, int S_ba
   const long long sS = (S_batch == 1) ? 0 : (long long)D * D;
   if (launch_loss_terms(theta, S, sS, logdet, B, D, Bdiv, lpart, lossb, loss_out,
                         reinterpret_cast<unsigned*>(counter), st)) return 1;
+  if (grad_theta && ns_use_tc()) {
+    const int ldp = (D + 3) & ~3;
+    const size_t n2p = al4((size_t)B * D * ldp);
+    float* sp = escr + al4(eig_scratch_floats(B, D));
+    return spectral_recon_tc(Vt, f, grad_theta, B, D, ldp, n2p, sp, 1.0f / Bdiv, S, sS, 1.0f / Bdiv, st);
+  }
   if (grad_theta) return spectral_recon(Vt, f, grad_theta, B, D, 1.0f / Bdiv, S, sS, st);
   return 0;
 }
