@@ -9,7 +9,8 @@ constexpr int EW_THREADS = 256;
 
 int elem_blocks_per_graph(int D) {
   const long long n = (long long)D * D;
-  long long b = (n + 2047) / 2048;
+  long long b = (n + 4095) / 4096;
+  if (b < (D + 31) / 32) b = (D + 31) / 32;   // the large-D backward parks one trace partial per 32-row tile
   if (b < 1) b = 1;
   if (b > 512) b = 512;   // D = 1000: 489 blocks, enough to cover the 148 SMs several times
   return (int)b;
@@ -191,14 +192,26 @@ __global__ void __launch_bounds__(EW_THREADS) z_update_bwd_kernel(
     }
     GF3[base + i] = gt;
   }
-  float* out = rho_part + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * NPR;
+  // block reduction of the NPR accumulators: shuffles inside each warp first, ONE barrier, then a
+  // fixed-order sum over the warps (deterministic)
+  __shared__ float wred[EW_THREADS / 32][NPR_MAX];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
   for (int p = 0; p < NPR_MAX; ++p) {
     if (p < NPR) {
-      const float tot = block_sum(g[p], red);
-      if (threadIdx.x == 0) out[p] = tot;
+      const float tot = warp_sum(g[p]);
+      if (lane == 0) wred[wid][p] = tot;
     }
   }
+  __syncthreads();
+  float* out = rho_part + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * NPR;
+  if (threadIdx.x < NPR) {
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < EW_THREADS / 32; ++w) tot += wred[w][threadIdx.x];
+    out[threadIdx.x] = tot;
+  }
+  (void)red;
 }
 int launch_z_update_bwd(const float* GZ, const float* X, const float* S, const float* Tprev,
                         const float* params, int H, int B, int D, float* GX, float* GF3,
