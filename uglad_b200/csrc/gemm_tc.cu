@@ -14,6 +14,11 @@
 //              operand pairings per K granule, accumulating in TMEM; tcgen05.commit frees the slab
 //   warps 2-5: epilogue     -- tcgen05.ld of the accumulator (two TMEM stages, so the next tile's
 //              MMAs overlap), alpha/beta/diag epilogue, hi/lo split, vectorised stores
+// A launch carries one product or two independent products of the same shape (two sets of tensor
+// maps and epilogue parameters): the second doubles the tiles the persistent grid can spread over
+// 148 SMs.  Launches are chained with programmatic dependent launch: the prologue (barriers, TMEM
+// allocation, descriptor prefetch) runs under the tail of the previous kernel, griddepcontrol.wait
+// guards the first access to its results.
 #include <cuda.h>
 #include <mutex>
 #include <unordered_map>
