@@ -2,7 +2,9 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-import bench
+import bench, ctypes
+from uglad_b200 import _lib
+lib = _lib.load()
 from uglad_b200 import main as ug, ops
 from uglad_b200.utils import prepare_data
 key, vals, B, D = sys.argv[1], [int(sys.argv[2]), int(sys.argv[3])], int(sys.argv[4]), int(sys.argv[5])
@@ -25,4 +27,13 @@ for v in vals + vals:
     e0.record()
     for _ in range(5): l = step()
     e1.record(); torch.cuda.synchronize()
-    print(f"B={B} D={D} {key}={v}: step {e0.elapsed_time(e1)/5:.3f} ms loss {l.item():.5f}", flush=True)
+    msg = f"B={B} D={D} {key}={v}: step {e0.elapsed_time(e1)/5:.3f} ms loss {l.item():.5f}"
+    lib.uglad_profile(1, None, None)   # per-kernel CUDA-event brackets (serialises the launches a little)
+    for _ in range(2): step()
+    torch.cuda.synchronize()
+    for kind, name in ((0, "eig"), (1, "tc_gemm")):
+        k_ms, k_n, k_w = ctypes.c_double(0), ctypes.c_ulonglong(0), ctypes.c_double(0)
+        lib.uglad_profile_read(kind, ctypes.byref(k_ms), ctypes.byref(k_n), ctypes.byref(k_w))
+        if k_n.value: msg += f" | {name}: {k_ms.value/2:.2f} ms/step in {k_n.value//2} launches ({k_ms.value/k_n.value*1e3:.1f} us each)"
+    lib.uglad_profile(0, None, None)
+    print(msg, flush=True)

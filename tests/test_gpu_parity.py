@@ -283,31 +283,38 @@ def test_size_independent_properties_at_full_size(dev):
 
 
 # ---- large-D path (Newton-Schulz as dense products + blocked Cholesky) ---------------------------
-@pytest.fixture(params=[1, 0], ids=["tcgen05", "simt"])
+@pytest.fixture(params=[(1, 1), (1, 0), (0, 1)], ids=["tcgen05-raw", "tcgen05-presplit", "simt"])
 def force_large_path(request):
     """Lower the eigensolver/large-D threshold to 0 so that the large-D kernels run on the small
-    golden problems too (the threshold only selects the algorithm, never the result); both
-    product back-ends: tcgen05 3xTF32 (the default) and the FP32 SIMT kernel."""
+    golden problems too (the threshold only selects the algorithm, never the result); every
+    product back-end: tcgen05 3xTF32 on plain operands split in shared memory (the default), on
+    pre-split hi/lo pairs, and the FP32 SIMT kernel."""
     from uglad_b200 import ops
     ops.tune("small_d_max", 0)
-    ops.tune("use_tc", request.param)
+    ops.tune("use_tc", request.param[0])
+    ops.tune("tc_raw", request.param[1])
     ops.reset_warm_start()
     yield
     ops.tune("small_d_max", 166)
     ops.tune("use_tc", 1)
+    ops.tune("tc_raw", 1)
     ops.reset_warm_start()
 
 
 @pytest.mark.parametrize("M,N,K,batch,bn", [
     (128, 128, 32, 1, 0), (100, 100, 100, 3, 0), (7, 5, 3, 2, 0), (200, 200, 200, 2, 0), (130, 70, 45, 2, 64),
-    (300, 260, 129, 1, 112), (256, 256, 256, 1, 128), (1000, 1000, 1000, 1, 0), (100, 100, 100, 300, 0)])
-def test_tcgen05_3xtf32_gemm(dev, M, N, K, batch, bn):
+    (300, 260, 129, 1, 112), (256, 256, 256, 1, 128), (1000, 1000, 1000, 1, 0), (100, 100, 100, 300, 0),
+    (300, 260, 132, 1, 112), (130, 70, 44, 2, 64), (129, 250, 520, 2, 128)])
+@pytest.mark.parametrize("raw", [1, 0], ids=["raw", "presplit"])
+def test_tcgen05_3xtf32_gemm(dev, M, N, K, batch, bn, raw):
     """C = alpha A B^T + beta E1 + diag I on the tensor pipe against float64 numpy: FP32-class
-    accuracy (3xTF32), ragged edges, batches larger than the SM count, every tile width."""
+    accuracy (3xTF32), ragged edges, batches larger than the SM count, every tile width; plain
+    operands split inside the kernel (K % 4 == 0) and pre-split pairs."""
     import ctypes as C
     from uglad_b200 import _lib, ops
     lib = _lib.load()
     ops.tune("tc_bn", bn)
+    ops.tune("tc_raw", raw)
     try:
         rng = np.random.default_rng(M * 7 + N)
         A = rng.standard_normal((batch, M, K)).astype(np.float32)
@@ -331,6 +338,7 @@ def test_tcgen05_3xtf32_gemm(dev, M, N, K, batch, bn):
         assert np.abs(got - ref).max() < tol, (np.abs(got - ref).max(), tol)
     finally:
         ops.tune("tc_bn", 0)
+        ops.tune("tc_raw", 1)
 
 
 @pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])

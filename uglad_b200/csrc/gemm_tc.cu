@@ -14,6 +14,18 @@
 //              operand pairings per K granule, accumulating in TMEM; tcgen05.commit frees the slab
 //   warps 2-5: epilogue     -- tcgen05.ld of the accumulator (two TMEM stages, so the next tile's
 //              MMAs overlap), alpha/beta/diag epilogue, hi/lo split, vectorised stores
+// Raw-operand mode (RAW = true; operands with lo == nullptr; the default of the Newton-Schulz chain):
+// the operands are plain FP32 matrices.  TMA brings ONE 4-byte word per element into the hi slot
+// of the stage; the tensor core reads a 32-bit container as TF32 by dropping the low 13 mantissa
+// bits, so the raw word IS the hi operand (hi = trunc(x)), and eight more warps (6-13) only write
+// lo = x - trunc(x) (exact) into the neighbouring slot behind a generic->async proxy fence.  Half
+// the L2->SM bytes, and every producer of the chain writes 4 instead of 8 bytes per element.
+// Two MMAs per K granule instead of three: B_hi and B_lo sit next to each other in the stage, so
+//   acc[:, 0:2BN] += A_hi * [B_hi ; B_lo]^T   (one instruction, N = 2 BN)
+//   acc[:, 0:BN]  += A_lo * B_hi^T
+// and the epilogue adds the two column halves.  A K = 8 TF32 instruction with both operands in
+// shared memory is bound by the 4 KB A-operand read (~65-78 cycles measured for N = 64 ... 128), so
+// the wide instruction costs no more than a narrow one until N/2 cycles of tensor work exceed it.
 // A launch carries one product or two independent products of the same shape (two sets of tensor
 // maps and epilogue parameters): the second doubles the tiles the persistent grid can spread over
 // 148 SMs.  Launches are chained with programmatic dependent launch: the prologue (barriers, TMEM
@@ -31,10 +43,22 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 32;                 // floats per K slab = one 128-byte swizzle row
 constexpr int A_BYTES = BM * BK * 4;   // 16 KB
-constexpr int THREADS = 192;
+constexpr int THREADS = 192;       // pre-split operands: TMA warp, MMA warp, 4 epilogue warps
+constexpr int SPLIT_WARPS = 8;     // raw operands: + 8 warps that split the slabs in shared memory
+constexpr int THREADS_RAW = THREADS + 32 * SPLIT_WARPS;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one leader lane of a converged warp; ptxas then treats the guarded region as single-threaded and
+// issues the tcgen05 / TMA instructions without a per-instruction election loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// the part of x that a TF32 read of its 32-bit container drops: lo = x - trunc_tf32(x) (exact)
+__device__ __forceinline__ float lo1(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+__device__ __forceinline__ float4 lo4(const float4& x) { return make_float4(lo1(x.x), lo1(x.y), lo1(x.z), lo1(x.w)); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -109,16 +133,37 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+// the two column halves of one accumulator chunk (columns c .. c+31 and c+off .. c+off+31), one wait
+__device__ __forceinline__ void tmem_ld32x2(uint32_t taddr, uint32_t off, uint32_t* r, uint32_t* r2) {
+  tmem_ld32_nowait(taddr, r);
+  tmem_ld32_nowait(taddr + off, r2);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 template <int BN>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int STAGES = (BN <= 64) ? 4 : 3;
-  static constexpr int TMEM_COLS = (BN <= 64) ? 128 : 256;  // two accumulator stages
+  static constexpr int TMEM_COLS = (BN <= 64) ? 256 : 512;  // two accumulator stages of 2 BN columns ([hi*hi + lo*hi | hi*lo])
   static constexpr int ACC_STRIDE = TMEM_COLS / 2;
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int RAW_TX_BYTES = A_BYTES + B_BYTES;   // raw mode: one word per element arrives by TMA
   // kind::tf32, FP32 accumulate, K-major A and B, M = 128, N = BN
   static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  static constexpr uint32_t IDESC2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // N = 2 BN
 };
 
 }  // namespace tc
@@ -136,14 +181,119 @@ struct TcEpi {
   int ldc;
 };
 struct TcParams {
-  long long* dbg;   // developer timeline: [grid][8] clock64 stamps (null = off)
+  long long* dbg;   // developer timeline: [grid][16] clock64 stamps and per-role phase sums (null = off)
   int M, N, K, batch, tiles_m, tiles_n;
   int nprob;        // 1, or 2: two independent products of the same shape share one launch
+  int exp;          // developer experiment (wrong results): 1 = pre-split kernel skips its TMA loads
   TcEpi e[2];
 };
 
+// epilogue of one tile by the four epilogue warps (warp quarter q owns TMEM lanes 32q .. 32q+31 =
+// tile rows): C = alpha acc + beta E1 + diag I, optional hi/lo split, vectorised stores
 template <int BN>
-__global__ void __launch_bounds__(tc::THREADS, 1)
+__device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, const TcEpi& ep, uint32_t tmem_acc, int tm, int tn,
+                                                 int b, int q, int lane) {
+  const bool vec_c = (ep.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.C_hi) & 15) == 0) &&
+                     (ep.C_lo == nullptr || (reinterpret_cast<uintptr_t>(ep.C_lo) & 15) == 0) && (ep.sC % 4 == 0);
+  const bool vec_e = ep.E1_hi != nullptr && (ep.lde1 % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.E1_hi) & 15) == 0) &&
+                     (ep.E1_lo == nullptr || (reinterpret_cast<uintptr_t>(ep.E1_lo) & 15) == 0) && (ep.sE1 % 4 == 0);
+  const int row = tm * tc::BM + q * 32 + lane;
+  const float alpha = ep.alpha_dev ? ep.alpha * ep.alpha_dev[b] : ep.alpha;
+  const float beta = ep.beta, diag = ep.diag;
+  float* Ch = ep.C_hi + (size_t)b * ep.sC + (size_t)row * ep.ldc;
+  float* Cl = ep.C_lo ? ep.C_lo + (size_t)b * ep.sC + (size_t)row * ep.ldc : nullptr;
+  const float* Eh = ep.E1_hi ? ep.E1_hi + (size_t)b * ep.sE1 + (size_t)row * ep.lde1 : nullptr;
+  const float* El = ep.E1_lo ? ep.E1_lo + (size_t)b * ep.sE1 + (size_t)row * ep.lde1 : nullptr;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    uint32_t v[32], v2[32];
+    tc::tmem_ld32x2(tmem_acc + ((uint32_t)(q * 32) << 16) + c0, BN, v, v2);
+    if (row < p.M) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const int col = tn * BN + c0 + j;
+        if (c0 + j >= BN || col >= p.N) break;   // BN = 112: the last 32-column read overhangs the tile
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = alpha * (__uint_as_float(v[j + e]) + __uint_as_float(v2[j + e]));
+        const bool full4 = col + 3 < p.N;
+        if (Eh) {
+          if (full4 && vec_e) {
+            const float4 eh = *reinterpret_cast<const float4*>(Eh + col);
+            o[0] = fmaf(beta, eh.x, o[0]); o[1] = fmaf(beta, eh.y, o[1]);
+            o[2] = fmaf(beta, eh.z, o[2]); o[3] = fmaf(beta, eh.w, o[3]);
+            if (El) {
+              const float4 el = *reinterpret_cast<const float4*>(El + col);
+              o[0] = fmaf(beta, el.x, o[0]); o[1] = fmaf(beta, el.y, o[1]);
+              o[2] = fmaf(beta, el.z, o[2]); o[3] = fmaf(beta, el.w, o[3]);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (col + e < p.N) {
+                float ev = Eh[col + e];
+                if (El) ev += El[col + e];
+                o[e] = fmaf(beta, ev, o[e]);
+              }
+          }
+        }
+        if (diag != 0.f) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (col + e == row) o[e] += diag;
+        }
+        if (Cl) {
+          float h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            uint32_t hb;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(o[e]));
+            h[e] = __uint_as_float(hb);
+            l[e] = o[e] - h[e];
+          }
+          if (full4 && vec_c) {
+            *reinterpret_cast<float4*>(Ch + col) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(Cl + col) = make_float4(l[0], l[1], l[2], l[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (col + e < p.N) { Ch[col + e] = h[e]; Cl[col + e] = l[e]; }
+          }
+        } else {
+          if (full4 && vec_c) {
+            *reinterpret_cast<float4*>(Ch + col) = make_float4(o[0], o[1], o[2], o[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (col + e < p.N) Ch[col + e] = o[e];
+          }
+        }
+      }
+    }
+  }
+}
+
+// the MMAs of one K slab: operand set (Ah | Al | Bh | Bl) OFF bytes behind the slab descriptor d0.
+// OFF is a compile-time constant, so every descriptor is d0 + immediate (the 14-bit address field
+// cannot carry: shared-memory addresses stay below 256 KB).
+template <int BN, int OFF>
+__device__ __forceinline__ void tc_issue_slab(uint64_t d0, uint32_t tmem_d, int ngran, bool first_slab) {
+  using C = tc::Cfg<BN>;
+  constexpr uint64_t oAh = (uint64_t)(OFF >> 4), oAl = (uint64_t)((OFF + tc::A_BYTES) >> 4),
+                     oBh = (uint64_t)((OFF + 2 * tc::A_BYTES) >> 4);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    if (g < ngran) {
+      const uint64_t adv = (uint64_t)(g * 2);                 // 32 bytes >> 4 inside the swizzle row
+      // [B_hi ; B_lo] is one K-major operand of 2 BN rows (8-row groups 1024 bytes apart throughout)
+      tc::umma_tf32(tmem_d, d0 + oAh + adv, d0 + oBh + adv, C::IDESC2, (g != 0 || !first_slab) ? 1u : 0u);
+      tc::umma_tf32(tmem_d, d0 + oAl + adv, d0 + oBh + adv, C::IDESC, 1u);
+    }
+  }
+}
+
+template <int BN, bool RAW>
+__global__ void __launch_bounds__(RAW ? tc::THREADS_RAW : tc::THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                const __grid_constant__ CUtensorMap tm2Ah, const __grid_constant__ CUtensorMap tm2Al,
@@ -155,15 +305,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   uint8_t* smem = smem_raw + (base - raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
   const uint32_t bar0 = base + C::STAGES * C::STAGE_BYTES;
-  // barrier slots: full[STAGES] | empty[STAGES] | tmem_full[2] | tmem_empty[2] | tmem base address
+  // barrier slots: full[STAGES] | empty[STAGES] | tmem_full[2] | tmem_empty[2] | tmem base address | split[STAGES]
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (C::STAGES + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * C::STAGES + a); };
   auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * C::STAGES + 2 + a); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * C::STAGES + 4);
+  auto split_bar = [&](int s) { return bar0 + 8u * (2 * C::STAGES + 5 + s); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 8 : nullptr;
+  long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 16 : nullptr;
   if (dbg && threadIdx.x == 0) {
     dbg[0] = clock64();
     unsigned long long gt;
@@ -179,6 +330,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     }
     for (int s = 0; s < C::STAGES; ++s) { tc::mbar_init(full_bar(s), 1); tc::mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { tc::mbar_init(tfull_bar(a), 1); tc::mbar_init(tempty_bar(a), 4); }
+    if (RAW) for (int s = 0; s < C::STAGES; ++s) tc::mbar_init(split_bar(s), tc::SPLIT_WARPS / 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -205,7 +357,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   const int num_kb = (p.K + tc::BK - 1) / tc::BK;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int b = tile / tiles_per_batch, r0 = tile - b * tiles_per_batch;
@@ -218,48 +370,94 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         for (int kb = 0; kb < num_kb; ++kb) {
           tc::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = base + stage * C::STAGE_BYTES;
-          tc::mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          if (p.exp & 1) { tc::mbar_arrive(full_bar(stage)); if (++stage == C::STAGES) { stage = 0; phase ^= 1u; } continue; }
+          tc::mbar_arrive_expect_tx(full_bar(stage), RAW ? C::RAW_TX_BYTES : C::STAGE_BYTES);
           tc::tma_load_3d(sa, mAh, full_bar(stage), kb * tc::BK, tm * tc::BM, b);
-          tc::tma_load_3d(sa + tc::A_BYTES, mAl, full_bar(stage), kb * tc::BK, tm * tc::BM, b);
+          if (!RAW) tc::tma_load_3d(sa + tc::A_BYTES, mAl, full_bar(stage), kb * tc::BK, tm * tc::BM, b);
           tc::tma_load_3d(sa + 2 * tc::A_BYTES, mBh, full_bar(stage), kb * tc::BK, tn * BN, b);
-          tc::tma_load_3d(sa + 2 * tc::A_BYTES + C::B_BYTES, mBl, full_bar(stage), kb * tc::BK, tn * BN, b);
+          if (!RAW) tc::tma_load_3d(sa + 2 * tc::A_BYTES + C::B_BYTES, mBl, full_bar(stage), kb * tc::BK, tn * BN, b);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
+      const uint64_t d0 = tc::umma_desc(base);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         tc::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc::tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * C::ACC_STRIDE;
+        long long tw = 0, ti = 0, tcm = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
-          tc::mbar_wait(full_bar(stage), phase);
+          const long long c0 = dbg ? clock64() : 0;
+          tc::mbar_wait(RAW ? split_bar(stage) : full_bar(stage), phase);
           tc::tc_fence_after();
-          if (dbg && kb == 0 && tile == (int)blockIdx.x) dbg[3] = clock64();
-          const uint32_t sa = base + stage * C::STAGE_BYTES;
-          const uint64_t dAh = tc::umma_desc(sa), dAl = tc::umma_desc(sa + tc::A_BYTES);
-          const uint64_t dBh = tc::umma_desc(sa + 2 * tc::A_BYTES), dBl = tc::umma_desc(sa + 2 * tc::A_BYTES + C::B_BYTES);
+          const long long c1 = dbg ? clock64() : 0;
+          if (dbg && kb == 0 && tile == (int)blockIdx.x) dbg[3] = c1;
           const int krem = p.K - kb * tc::BK;
           const int ngran = krem >= tc::BK ? 4 : (krem + 7) >> 3;   // K granules of 8 that hold data
-          for (int g = 0; g < ngran; ++g) {
-            const uint64_t adv = (uint64_t)(g * 2);                 // 32 bytes >> 4 inside the swizzle row
-            tc::umma_tf32(tmem_d, dAl + adv, dBh + adv, C::IDESC, (kb | g) != 0);
-            tc::umma_tf32(tmem_d, dAh + adv, dBl + adv, C::IDESC, 1u);
-            tc::umma_tf32(tmem_d, dAh + adv, dBh + adv, C::IDESC, 1u);
+          switch (stage) {
+            case 0: tc_issue_slab<BN, 0>(d0, tmem_d, ngran, kb == 0); break;
+            case 1: tc_issue_slab<BN, C::STAGE_BYTES>(d0, tmem_d, ngran, kb == 0); break;
+            case 2: tc_issue_slab<BN, 2 * C::STAGE_BYTES>(d0, tmem_d, ngran, kb == 0); break;
+            default: tc_issue_slab<BN, (C::STAGES - 1) * C::STAGE_BYTES>(d0, tmem_d, ngran, kb == 0); break;
           }
+          const long long c2 = dbg ? clock64() : 0;
           tc::umma_commit(empty_bar(stage));
+          if (dbg) { const long long c3 = clock64(); tw += c1 - c0; ti += c2 - c1; tcm += c3 - c2; }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
+        if (dbg && tile == (int)blockIdx.x) { dbg[8] = tw; dbg[9] = ti; dbg[10] = tcm; }
         tc::umma_commit(tfull_bar(acc));
         if (dbg && tile == (int)blockIdx.x) dbg[4] = clock64();
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
     __syncwarp();
+  } else if (RAW && warp >= 6) {
+    // split warps: lo = x - trunc_tf32(x) next to the raw slab (which the tensor core reads as hi).
+    // The 128B swizzle permutes 16-byte chunks identically in the hi and lo slots, so the pass is a
+    // flat elementwise walk over the raw bytes.
+    // Two groups of four warps take alternate slabs, so that the wait -> load -> store -> fence ->
+    // arrive latency chain of one slab overlaps the next one's.
+    constexpr int NT = 32 * tc::SPLIT_WARPS / 2;
+    const int t = (threadIdx.x - tc::THREADS) % NT, grp = (threadIdx.x - tc::THREADS) / NT;
+    constexpr int A_CH = tc::A_BYTES / 16, B_CH = C::B_BYTES / 16;   // 16-byte chunks per slab
+    const long long my_tiles = total_tiles > (int)blockIdx.x ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const long long nslab = my_tiles * num_kb;
+    long long tw = 0, tcv = 0;
+    for (long long i = grp; i < nslab; i += 2) {
+      const int stage = (int)(i % C::STAGES);
+      const uint32_t phase = (uint32_t)((i / C::STAGES) & 1);
+      const long long c0 = dbg ? clock64() : 0;
+      tc::mbar_wait(full_bar(stage), phase);
+      const long long c1 = dbg ? clock64() : 0;
+      uint8_t* sa = smem + stage * C::STAGE_BYTES;
+      const float4* a_hi = reinterpret_cast<const float4*>(sa);
+      float4* a_lo = reinterpret_cast<float4*>(sa + tc::A_BYTES);
+      const float4* b_hi = reinterpret_cast<const float4*>(sa + 2 * tc::A_BYTES);
+      float4* b_lo = reinterpret_cast<float4*>(sa + 2 * tc::A_BYTES + C::B_BYTES);
+      float4 xa[A_CH / NT];
+#pragma unroll
+      for (int j = 0; j < A_CH / NT; ++j) xa[j] = a_hi[t + j * NT];
+#pragma unroll
+      for (int j = 0; j < A_CH / NT; ++j) a_lo[t + j * NT] = tc::lo4(xa[j]);
+      float4 xb[(B_CH + NT - 1) / NT];
+#pragma unroll
+      for (int j = 0; j < (B_CH + NT - 1) / NT; ++j)
+        if (B_CH % NT == 0 || t + j * NT < B_CH) xb[j] = b_hi[t + j * NT];
+#pragma unroll
+      for (int j = 0; j < (B_CH + NT - 1) / NT; ++j)
+        if (B_CH % NT == 0 || t + j * NT < B_CH) b_lo[t + j * NT] = tc::lo4(xb[j]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tensor-core (async proxy) reads
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(split_bar(stage));
+      if (dbg) { const long long c2 = clock64(); tw += c1 - c0; tcv += c2 - c1; }
+    }
+    if (dbg && t == 0 && grp == 0) { dbg[11] = tw; dbg[12] = 0; dbg[13] = tcv; }
   } else {
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     int acc = 0; uint32_t acc_phase = 0;
@@ -268,87 +466,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       const int prob = r0 / tiles_per_prob, r = r0 - prob * tiles_per_prob;
       const int tm = r / p.tiles_n, tn = r - tm * p.tiles_n;
       const TcEpi& ep = p.e[prob];
-      const bool vec_c = (ep.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.C_hi) & 15) == 0) &&
-                         (ep.C_lo == nullptr || (reinterpret_cast<uintptr_t>(ep.C_lo) & 15) == 0) && (ep.sC % 4 == 0);
-      const bool vec_e = ep.E1_hi != nullptr && (ep.lde1 % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.E1_hi) & 15) == 0) &&
-                         (ep.E1_lo == nullptr || (reinterpret_cast<uintptr_t>(ep.E1_lo) & 15) == 0) && (ep.sE1 % 4 == 0);
       tc::mbar_wait(tfull_bar(acc), acc_phase);
       tc::tc_fence_after();
       if (dbg && tile == (int)blockIdx.x && warp == 2 && lane == 0) dbg[5] = clock64();
-      const int row = tm * tc::BM + q * 32 + lane;
-      const float alpha = ep.alpha_dev ? ep.alpha * ep.alpha_dev[b] : ep.alpha;
-      const float beta = ep.beta, diag = ep.diag;
-      float* Ch = ep.C_hi + (size_t)b * ep.sC + (size_t)row * ep.ldc;
-      float* Cl = ep.C_lo ? ep.C_lo + (size_t)b * ep.sC + (size_t)row * ep.ldc : nullptr;
-      const float* Eh = ep.E1_hi ? ep.E1_hi + (size_t)b * ep.sE1 + (size_t)row * ep.lde1 : nullptr;
-      const float* El = ep.E1_lo ? ep.E1_lo + (size_t)b * ep.sE1 + (size_t)row * ep.lde1 : nullptr;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::ACC_STRIDE + c0, v);
-        if (row < p.M) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const int col = tn * BN + c0 + j;
-            if (c0 + j >= BN || col >= p.N) break;   // BN = 112: the last 32-column read overhangs the tile
-            float o[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) o[e] = alpha * __uint_as_float(v[j + e]);
-            const bool full4 = col + 3 < p.N;
-            if (Eh) {
-              if (full4 && vec_e) {
-                const float4 eh = *reinterpret_cast<const float4*>(Eh + col);
-                o[0] = fmaf(beta, eh.x, o[0]); o[1] = fmaf(beta, eh.y, o[1]);
-                o[2] = fmaf(beta, eh.z, o[2]); o[3] = fmaf(beta, eh.w, o[3]);
-                if (El) {
-                  const float4 el = *reinterpret_cast<const float4*>(El + col);
-                  o[0] = fmaf(beta, el.x, o[0]); o[1] = fmaf(beta, el.y, o[1]);
-                  o[2] = fmaf(beta, el.z, o[2]); o[3] = fmaf(beta, el.w, o[3]);
-                }
-              } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  if (col + e < p.N) {
-                    float ev = Eh[col + e];
-                    if (El) ev += El[col + e];
-                    o[e] = fmaf(beta, ev, o[e]);
-                  }
-              }
-            }
-            if (diag != 0.f) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (col + e == row) o[e] += diag;
-            }
-            if (Cl) {
-              float h[4], l[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                uint32_t hb;
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(o[e]));
-                h[e] = __uint_as_float(hb);
-                l[e] = o[e] - h[e];
-              }
-              if (full4 && vec_c) {
-                *reinterpret_cast<float4*>(Ch + col) = make_float4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<float4*>(Cl + col) = make_float4(l[0], l[1], l[2], l[3]);
-              } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  if (col + e < p.N) { Ch[col + e] = h[e]; Cl[col + e] = l[e]; }
-              }
-            } else {
-              if (full4 && vec_c) {
-                *reinterpret_cast<float4*>(Ch + col) = make_float4(o[0], o[1], o[2], o[3]);
-              } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  if (col + e < p.N) Ch[col + e] = o[e];
-              }
-            }
-          }
-        }
-      }
+      tc_epilogue_tile<BN>(p, ep, tmem_base + acc * C::ACC_STRIDE, tm, tn, b, q, lane);
       tc::tc_fence_before();
       __syncwarp();
       if (dbg && tile == (int)blockIdx.x && warp == 2 && lane == 0) dbg[6] = clock64();
@@ -369,6 +490,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
   }
 }
+
 
 // ---------------------------------------------------------------------------------------------
 // host side: tensor maps (cached: the operands live in a handful of fixed scratch matrices)
@@ -443,6 +565,11 @@ static int g_tc_bn = 0;   // 0 = auto
 static int g_tc_pdl = 1;  // programmatic dependent launch between the chained products
 int tc_tune_bn(int bn) { g_tc_bn = bn; return 0; }
 int tc_tune_pdl(int on) { g_tc_pdl = on; return 0; }
+static int g_tc_raw = 1;   // plain FP32 operands, hi/lo split inside the kernel (0: pre-split pairs in HBM)
+int tc_tune_raw(int on) { g_tc_raw = on ? 1 : 0; return 0; }
+bool tc_raw_enabled() { return g_tc_raw != 0; }
+static int g_tc_exp = 0;
+int tc_tune_exp(int v) { g_tc_exp = v; return 0; }
 static int g_tc_dual = 1;  // pair independent same-shape products into one launch
 int tc_tune_dual(int on) { g_tc_dual = on; return 0; }
 static long long* g_tc_dbg = nullptr;   // developer timeline buffer (uglad_tc_debug_buffer)
@@ -455,12 +582,12 @@ static void fill_epi(TcEpi& e, const TcGemm& g) {
 }
 
 // g2 == nullptr: one product; otherwise two independent products of identical shape in one launch
-template <int BN>
+template <int BN, bool RAW>
 static int launch_tc(const TcGemm& g, const TcGemm* g2, int batch, cudaStream_t st) {
   using C = tc::Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    UGLAD_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    UGLAD_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     attr_set = true;
   }
   CUtensorMap m[8];
@@ -468,9 +595,14 @@ static int launch_tc(const TcGemm& g, const TcGemm* g2, int batch, cudaStream_t 
   for (int i = 0; i < 2; ++i) {
     const TcGemm& q = *gs[i];
     if (get_map(q.A_hi, q.M, q.K, q.lda, batch, q.sA, tc::BM, &m[4 * i + 0])) return 1;
-    if (get_map(q.A_lo, q.M, q.K, q.lda, batch, q.sA, tc::BM, &m[4 * i + 1])) return 1;
     if (get_map(q.B_hi, q.N, q.K, q.ldb, batch, q.sB, BN, &m[4 * i + 2])) return 1;
-    if (get_map(q.B_lo, q.N, q.K, q.ldb, batch, q.sB, BN, &m[4 * i + 3])) return 1;
+    if (RAW) {   // plain operands: the lo maps are never dereferenced
+      m[4 * i + 1] = m[4 * i + 0];
+      m[4 * i + 3] = m[4 * i + 2];
+    } else {
+      if (get_map(q.A_lo, q.M, q.K, q.lda, batch, q.sA, tc::BM, &m[4 * i + 1])) return 1;
+      if (get_map(q.B_lo, q.N, q.K, q.ldb, batch, q.sB, BN, &m[4 * i + 3])) return 1;
+    }
   }
   TcParams p;
   p.dbg = g_tc_dbg;
@@ -478,6 +610,7 @@ static int launch_tc(const TcGemm& g, const TcGemm* g2, int batch, cudaStream_t 
   p.tiles_m = (g.M + tc::BM - 1) / tc::BM;
   p.tiles_n = (g.N + BN - 1) / BN;
   p.nprob = g2 ? 2 : 1;
+  p.exp = g_tc_exp;
   fill_epi(p.e[0], g);
   fill_epi(p.e[1], *gs[1]);
   const long long total = (long long)p.tiles_m * p.tiles_n * batch * p.nprob;
@@ -490,7 +623,7 @@ static int launch_tc(const TcGemm& g, const TcGemm* g2, int batch, cudaStream_t 
   profile_begin(st, 1, 2.0 * g.M * g.N * g.K * batch * p.nprob);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(tc::THREADS);
+  cfg.blockDim = dim3(RAW ? tc::THREADS_RAW : tc::THREADS);
   cfg.dynamicSmemBytes = C::SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -498,7 +631,7 @@ static int launch_tc(const TcGemm& g, const TcGemm* g2, int batch, cudaStream_t 
   attr[0].val.programmaticStreamSerializationAllowed = g_tc_pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  UGLAD_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN>, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], p));
+  UGLAD_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, RAW>, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], p));
   profile_end(st);
   UGLAD_CHECK_LAUNCH("tc_gemm_kernel");
   return 0;
@@ -506,16 +639,22 @@ static int launch_tc(const TcGemm& g, const TcGemm* g2, int batch, cudaStream_t 
 
 bool tc_gemm_supported(const TcGemm& g) {
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  // both operands pre-split (hi + lo) or both plain (lo == nullptr: split inside the kernel)
   return g.lda % 4 == 0 && g.ldb % 4 == 0 && g.sA % 4 == 0 && g.sB % 4 == 0 && al16(g.A_hi) && al16(g.A_lo) &&
-         al16(g.B_hi) && al16(g.B_lo) && g.M > 0 && g.N > 0 && g.K > 0;
+         al16(g.B_hi) && al16(g.B_lo) && g.A_hi && g.B_hi && ((g.A_lo == nullptr) == (g.B_lo == nullptr)) &&
+         g.M > 0 && g.N > 0 && g.K > 0;
 }
 
 static int launch_tc_any(const TcGemm& g, const TcGemm* g2, int batch, cudaStream_t st) {
   if (!tc_gemm_supported(g) || (g2 && !tc_gemm_supported(*g2))) {
-    set_error("tc_gemm: operands must be 16-byte aligned with ld %% 4 == 0");
+    set_error("tc_gemm: operands must be 16-byte aligned with ld %% 4 == 0, both split or both plain");
     return 1;
   }
-  if (g2 && (g2->M != g.M || g2->N != g.N || g2->K != g.K)) { set_error("tc_gemm: dual launch needs identical shapes"); return 1; }
+  if (g2 && (g2->M != g.M || g2->N != g.N || g2->K != g.K || (g2->A_lo == nullptr) != (g.A_lo == nullptr))) {
+    set_error("tc_gemm: dual launch needs identical shapes and operand forms");
+    return 1;
+  }
+  const bool raw = g.A_lo == nullptr;
   if (batch <= 0) return 0;
   if (g_num_sms == 0) {
     int dev = 0;
@@ -542,9 +681,9 @@ static int launch_tc_any(const TcGemm& g, const TcGemm* g2, int batch, cudaStrea
     }
   }
   switch (bn) {
-    case 64: return launch_tc<64>(g, g2, batch, st);
-    case 112: return launch_tc<112>(g, g2, batch, st);
-    case 128: return launch_tc<128>(g, g2, batch, st);
+    case 64: return raw ? launch_tc<64, true>(g, g2, batch, st) : launch_tc<64, false>(g, g2, batch, st);
+    case 112: return raw ? launch_tc<112, true>(g, g2, batch, st) : launch_tc<112, false>(g, g2, batch, st);
+    case 128: return raw ? launch_tc<128, true>(g, g2, batch, st) : launch_tc<128, false>(g, g2, batch, st);
   }
   set_error("tc_gemm: unsupported tile width %d", bn);
   return 1;

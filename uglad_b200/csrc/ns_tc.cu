@@ -1,7 +1,8 @@
 // Large-D theta update on the tensor pipe: the Newton-Schulz chain of ns_large.cu with every
-// product issued as a tcgen05 3xTF32 GEMM (gemm_tc.cu).  All intermediates are "split" matrices
-// (hi = tf32(x), lo = x - hi; [B][D][ldp] with ldp = D rounded up to 4 so that TMA row strides are
-// 16-byte multiples).  The GEMM computes X Y^T; every right-hand operand of the chain is
+// product issued as a tcgen05 3xTF32 GEMM (gemm_tc.cu).  Intermediates are [B][D][ldp] matrices with
+// ldp = D rounded up to 4 (TMA row strides must be 16-byte multiples): plain FP32 in the default
+// raw-operand mode (the GEMM splits hi/lo in shared memory; SplitMat::lo == nullptr), or pre-split
+// pairs (hi = tf32(x), lo = x - hi) behind uglad_tune("tc_raw", 0).  The GEMM computes X Y^T; every right-hand operand of the chain is
 // symmetric (a polynomial in b, or A / Q / H + H^T of the backward), or antisymmetric
 // (W = A Q - Q A, where the sign flips), so no transposes are ever materialised:
 //   forward   A = b b ; Y1 = (A/n) T0 ; { T = (3I - Z Y)/2 ; Y <- Y T ; Z <- T Z } ; X = (sqrt(n) Y T - b)/2
@@ -20,6 +21,18 @@ __device__ __forceinline__ void split_tf32(float v, float& h, float& l) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
   h = __uint_as_float(hb);
   l = v - h;
+}
+// element access of a matrix that is either plain (lo == nullptr) or a hi/lo pair
+__device__ __forceinline__ float sp_ld(const float* h, const float* l, size_t o) { return l ? h[o] + l[o] : h[o]; }
+__device__ __forceinline__ void sp_st(float* h, float* l, size_t o, float v) {
+  if (l) {
+    float hh, ll;
+    split_tf32(v, hh, ll);
+    h[o] = hh;
+    l[o] = ll;
+  } else {
+    h[o] = v;
+  }
 }
 
 __device__ __forceinline__ void tcs_finish_norm(float tot, float* part, unsigned* counter, float* scal, int B,
@@ -57,10 +70,7 @@ __global__ void __launch_bounds__(TCS_THREADS) tcs_build_b_kernel(const float* _
   const size_t base = (size_t)blockIdx.y * n, pbase = (size_t)blockIdx.y * D * ldp;
   for (int i = blockIdx.x * TCS_THREADS + threadIdx.x; i < n; i += gridDim.x * TCS_THREADS) {
     const int r = i / D, c = i - r * D;
-    float h, l;
-    split_tf32(fmaf(il, Sb[i], -Theta[base + i]), h, l);
-    bh[pbase + (size_t)r * ldp + c] = h;
-    bl[pbase + (size_t)r * ldp + c] = l;
+    sp_st(bh, bl, pbase + (size_t)r * ldp + c, fmaf(il, Sb[i], -Theta[base + i]));
   }
 }
 
@@ -78,13 +88,10 @@ __global__ void __launch_bounds__(TCS_THREADS) tcs_diag_fro_kernel(float* __rest
   for (int i = blockIdx.x * TCS_THREADS + threadIdx.x; i < n; i += gridDim.x * TCS_THREADS) {
     const int r = i / D, c = i - r * D;
     const size_t o = pbase + (size_t)r * ldp + c;
-    float v = Ah[o] + Al[o];
+    float v = sp_ld(Ah, Al, o);
     if (r == c) {
       v += c4;
-      float h, l;
-      split_tf32(v, h, l);
-      Ah[o] = h;
-      Al[o] = l;
+      sp_st(Ah, Al, o, v);
     }
     acc = fmaf(v, v, acc);
   }
@@ -102,10 +109,7 @@ __global__ void __launch_bounds__(TCS_THREADS) tcs_t0_kernel(const float* __rest
   for (int i = blockIdx.x * TCS_THREADS + threadIdx.x; i < n; i += gridDim.x * TCS_THREADS) {
     const int r = i / D, c = i - r * D;
     const size_t o = pbase + (size_t)r * ldp + c;
-    float h, l;
-    split_tf32(fmaf(hf, Ah[o] + Al[o], (r == c) ? 1.5f : 0.f), h, l);
-    Zh[o] = h;
-    Zl[o] = l;
+    sp_st(Zh, Zl, o, fmaf(hf, sp_ld(Ah, Al, o), (r == c) ? 1.5f : 0.f));
   }
 }
 
@@ -130,10 +134,7 @@ __global__ void __launch_bounds__(TCS_THREADS) tcs_build_r_kernel(const float* _
     const size_t o = pbase + (size_t)r * ldp + c;
     const float bv = fmaf(il, Sb[i], -Theta[base + i]);
     const float rv = fmaf(2.f, X[base + i], bv);
-    float h, l;
-    split_tf32(bv, h, l);
-    bh[o] = h;
-    bl[o] = l;
+    sp_st(bh, bl, o, bv);
     R[o] = rv;
     acc = fmaf(rv, rv, acc);
   }
@@ -152,13 +153,8 @@ __global__ void __launch_bounds__(TCS_THREADS) tcs_scale_aq_kernel(float* __rest
   for (int i = blockIdx.x * TCS_THREADS + threadIdx.x; i < n; i += gridDim.x * TCS_THREADS) {
     const int r = i / D, c = i - r * D;
     const size_t o = pbase + (size_t)r * ldp + c;
-    float h, l;
-    split_tf32(Ah[o] * inv, h, l);
-    Ah[o] = h;
-    Al[o] = l;
-    split_tf32(GX[base + i] * (0.5f * inv), h, l);
-    Qh[o] = h;
-    Ql[o] = l;
+    sp_st(Ah, Al, o, Ah[o] * inv);
+    sp_st(Qh, Ql, o, GX[base + i] * (0.5f * inv));
   }
 }
 
@@ -172,7 +168,7 @@ __global__ void tcs_hsym_kernel(const float* __restrict__ Qh, const float* __res
   for (int r = threadIdx.y; r < 32; r += 8) {
     const int gi = bx + r, gj = by + threadIdx.x;
     const size_t o = pbase + (size_t)gi * ldp + gj;
-    t[r][threadIdx.x] = (gi < D && gj < D) ? Qh[o] + Ql[o] : 0.f;
+    t[r][threadIdx.x] = (gi < D && gj < D) ? sp_ld(Qh, Ql, o) : 0.f;
   }
   __syncthreads();
   float tr = 0.f;
@@ -180,11 +176,8 @@ __global__ void tcs_hsym_kernel(const float* __restrict__ Qh, const float* __res
     const int gi = by + r, gj = bx + threadIdx.x;
     if (gi < D && gj < D) {
       const size_t o = pbase + (size_t)gi * ldp + gj;
-      const float q = Qh[o] + Ql[o];
-      float h, l;
-      split_tf32(0.5f * (q + t[threadIdx.x][r]), h, l);
-      Hh[o] = h;
-      Hl[o] = l;
+      const float q = sp_ld(Qh, Ql, o);
+      sp_st(Hh, Hl, o, 0.5f * (q + t[threadIdx.x][r]));
       if (gi == gj) tr += 0.5f * q;
     }
   }
@@ -210,24 +203,19 @@ __global__ void tcs_antisym_kernel(float* __restrict__ Ph, float* __restrict__ P
     const int c = threadIdx.x;
     const size_t oa = pbase + (size_t)(bx + r) * ldp + by + c;   // tile (bx, by)
     const size_t ob = pbase + (size_t)(by + r) * ldp + bx + c;   // tile (by, bx)
-    ta[r][c] = (bx + r < D && by + c < D) ? Ph[oa] + Pl[oa] : 0.f;
-    tb[r][c] = (by + r < D && bx + c < D) ? Ph[ob] + Pl[ob] : 0.f;
+    ta[r][c] = (bx + r < D && by + c < D) ? sp_ld(Ph, Pl, oa) : 0.f;
+    tb[r][c] = (by + r < D && bx + c < D) ? sp_ld(Ph, Pl, ob) : 0.f;
   }
   __syncthreads();
   for (int r = threadIdx.y; r < 32; r += 8) {
     const int c = threadIdx.x;
-    float h, l;
     if (bx + r < D && by + c < D) {
       const size_t oa = pbase + (size_t)(bx + r) * ldp + by + c;
-      split_tf32(ta[r][c] - tb[c][r], h, l);
-      Ph[oa] = h;
-      Pl[oa] = l;
+      sp_st(Ph, Pl, oa, ta[r][c] - tb[c][r]);
     }
     if (blockIdx.x != blockIdx.y && by + r < D && bx + c < D) {
       const size_t ob = pbase + (size_t)(by + r) * ldp + bx + c;
-      split_tf32(tb[r][c] - ta[c][r], h, l);
-      Ph[ob] = h;
-      Pl[ob] = l;
+      sp_st(Ph, Pl, ob, tb[r][c] - ta[c][r]);
     }
   }
 }
@@ -278,9 +266,10 @@ static TcsBuf tcs_carve(float* scratch, int B, int D) {
   TcsBuf s;
   s.ldp = ldp_of(D);
   s.n2p = (long long)al4t((size_t)B * D * s.ldp);
+  const bool raw = tc_raw_enabled();
   for (int i = 0; i < 8; ++i) {
     s.M[i].hi = scratch + (size_t)(2 * i) * s.n2p;
-    s.M[i].lo = scratch + (size_t)(2 * i + 1) * s.n2p;
+    s.M[i].lo = raw ? nullptr : scratch + (size_t)(2 * i + 1) * s.n2p;
   }
   s.scal = scratch + 16 * (size_t)s.n2p;
   s.part = s.scal + al4t(3 * (size_t)B);
@@ -407,12 +396,20 @@ int tc_gemm_plain(const float* A, const float* Bm, const float* E1, float* C, in
   const int ldk = (K + 3) & ~3;
   const size_t na = al4t((size_t)batch * M * ldk), nb = al4t((size_t)batch * N * ldk);
   float *Ah = scratch, *Al = Ah + na, *Bh = Al + na, *Bl = Bh + nb;
-  if (launch_tcs_split(A, (long long)M * K, batch, M, K, K, ldk, Ah, Al, st)) return 1;
-  if (launch_tcs_split(Bm, (long long)N * K, batch, N, K, K, ldk, Bh, Bl, st)) return 1;
   TcGemm g;
-  g.A_hi = Ah; g.A_lo = Al; g.B_hi = Bh; g.B_lo = Bl;
-  g.M = M; g.N = N; g.K = K; g.lda = g.ldb = ldk;
-  g.sA = (long long)M * ldk; g.sB = (long long)N * ldk;
+  g.M = M; g.N = N; g.K = K;
+  const bool direct = tc_raw_enabled() && K % 4 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(Bm) & 15) == 0;
+  if (direct) {   // plain operands straight from the caller's buffers, split inside the kernel
+    g.A_hi = A; g.B_hi = Bm; g.lda = g.ldb = K;
+    g.sA = (long long)M * K; g.sB = (long long)N * K;
+  } else {
+    if (launch_tcs_split(A, (long long)M * K, batch, M, K, K, ldk, Ah, Al, st)) return 1;
+    if (launch_tcs_split(Bm, (long long)N * K, batch, N, K, K, ldk, Bh, Bl, st)) return 1;
+    g.A_hi = Ah; g.A_lo = Al; g.B_hi = Bh; g.B_lo = Bl;
+    g.lda = g.ldb = ldk;
+    g.sA = (long long)M * ldk; g.sB = (long long)N * ldk;
+  }
   g.alpha = alpha; g.beta = beta; g.diag = diag;
   g.E1_hi = E1; g.lde1 = N; g.sE1 = (long long)M * N;
   g.C_hi = C; g.ldc = N; g.sC = (long long)M * N;
@@ -425,12 +422,18 @@ int tc_gemm_repeat(const float* A, const float* Bm, float* C, int M, int N, int 
   const size_t na = al4t((size_t)batch * M * ldk), nb = al4t((size_t)batch * N * ldk);
   float *Ah = scratch, *Al = Ah + na, *Bh = Al + na, *Bl = Bh + nb;
   float* Cs = Bl + nb;   // split output region: 2 * batch * M * ldn
-  if (launch_tcs_split(A, (long long)M * K, batch, M, K, K, ldk, Ah, Al, st)) return 1;
-  if (launch_tcs_split(Bm, (long long)N * K, batch, N, K, K, ldk, Bh, Bl, st)) return 1;
   TcGemm g;
-  g.A_hi = Ah; g.A_lo = Al; g.B_hi = Bh; g.B_lo = Bl;
-  g.M = M; g.N = N; g.K = K; g.lda = g.ldb = ldk;
-  g.sA = (long long)M * ldk; g.sB = (long long)N * ldk;
+  g.M = M; g.N = N; g.K = K;
+  if (tc_raw_enabled() && K % 4 == 0) {
+    g.A_hi = A; g.B_hi = Bm; g.lda = g.ldb = K;
+    g.sA = (long long)M * K; g.sB = (long long)N * K;
+  } else {
+    if (launch_tcs_split(A, (long long)M * K, batch, M, K, K, ldk, Ah, Al, st)) return 1;
+    if (launch_tcs_split(Bm, (long long)N * K, batch, N, K, K, ldk, Bh, Bl, st)) return 1;
+    g.A_hi = Ah; g.A_lo = Al; g.B_hi = Bh; g.B_lo = Bl;
+    g.lda = g.ldb = ldk;
+    g.sA = (long long)M * ldk; g.sB = (long long)N * ldk;
+  }
   if (split_out) {
     g.C_hi = Cs; g.C_lo = Cs + al4t((size_t)batch * M * ldn); g.ldc = ldn; g.sC = (long long)M * ldn;
   } else {
