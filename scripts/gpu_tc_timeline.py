@@ -38,6 +38,7 @@ for i, n in enumerate(names):
 seg = np.diff(rel[:, :7], axis=1)
 print("  MMA thread, first tile (median cycles summed over the K slabs): wait %d, issue %d, commit %d" % tuple(np.median(used[:, 8 + i]) for i in range(3)))
 print("  split warps, first tile (raw-operand kernel): wait raw %d, wait split buffer %d, convert %d" % tuple(np.median(used[:, 11 + i]) for i in range(3)))
+print("  epilogue warp 2, first tile: tcgen05.ld + wait %d, math + stores %d" % tuple(np.median(used[:, 14 + i]) for i in range(2)))
 print("  per-CTA segments (median cycles):", {names[i + 1]: float(np.median(seg[:, i])) for i in range(6)})
 # back-to-back launches of the same product (no other kernels in between)
 for so in (0, 1):

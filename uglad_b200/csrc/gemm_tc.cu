@@ -43,9 +43,13 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 32;                 // floats per K slab = one 128-byte swizzle row
 constexpr int A_BYTES = BM * BK * 4;   // 16 KB
-constexpr int THREADS = 192;       // pre-split operands: TMA warp, MMA warp, 4 epilogue warps
+// epilogue warps: two per TMEM lane quarter for pre-split operands (a lone warp per scheduler is
+// latency-bound); the raw-operand kernel spends its register budget on eight split warps instead
+// (measured: 4 + 8 beats 8 + 4 and 8 + 8 there)
+constexpr int EPI_WARPS_SPLIT = 8, EPI_WARPS_RAW = 4;
+constexpr int THREADS = 64 + 32 * EPI_WARPS_SPLIT;   // pre-split operands: TMA warp, MMA warp, epilogue warps
 constexpr int SPLIT_WARPS = 8;     // raw operands: + 8 warps that split the slabs in shared memory
-constexpr int THREADS_RAW = THREADS + 32 * SPLIT_WARPS;
+constexpr int THREADS_RAW = 64 + 32 * EPI_WARPS_RAW + 32 * SPLIT_WARPS;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -55,6 +59,11 @@ __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
+}
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t hb;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
+  return __uint_as_float(hb);
 }
 // the part of x that a TF32 read of its 32-bit container drops: lo = x - trunc_tf32(x) (exact)
 __device__ __forceinline__ float lo1(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
@@ -68,8 +77,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   for (int spin = 0; !done; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"   // (a suspend-time hint was measured:
+        "selp.u32 %0, 1, 0, p;\n\t}"                                    // slower wake-ups, no gain in the chain)
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
@@ -159,7 +168,8 @@ struct Cfg {
   static constexpr int STAGES = (BN <= 64) ? 4 : 3;
   static constexpr int TMEM_COLS = (BN <= 64) ? 256 : 512;  // two accumulator stages of 2 BN columns ([hi*hi + lo*hi | hi*lo])
   static constexpr int ACC_STRIDE = TMEM_COLS / 2;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int EPI_BYTES = EPI_WARPS_SPLIT * 32 * 20 * 4;   // one 32 x 20 float patch per epilogue warp
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + EPI_BYTES;
   static constexpr int RAW_TX_BYTES = A_BYTES + B_BYTES;   // raw mode: one word per element arrives by TMA
   // kind::tf32, FP32 accumulate, K-major A and B, M = 128, N = BN
   static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -190,9 +200,11 @@ struct TcParams {
 
 // epilogue of one tile by the four epilogue warps (warp quarter q owns TMEM lanes 32q .. 32q+31 =
 // tile rows): C = alpha acc + beta E1 + diag I, optional hi/lo split, vectorised stores
-template <int BN>
+constexpr int EPI_LD = 20;   // floats per row of an epilogue warp's 32 x 16 patch (16-byte aligned rows, conflict-free row writes)
+template <int BN, int EPI_WARPS>
 __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, const TcEpi& ep, uint32_t tmem_acc, int tm, int tn,
-                                                 int b, int q, int lane) {
+                                                 int b, int q, int half, int lane, float* stg, long long* dbg) {
+  long long t_ld = 0, t_rest = 0;
   const bool vec_c = (ep.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.C_hi) & 15) == 0) &&
                      (ep.C_lo == nullptr || (reinterpret_cast<uintptr_t>(ep.C_lo) & 15) == 0) && (ep.sC % 4 == 0);
   const bool vec_e = ep.E1_hi != nullptr && (ep.lde1 % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.E1_hi) & 15) == 0) &&
@@ -204,10 +216,90 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, const TcEpi&
   float* Cl = ep.C_lo ? ep.C_lo + (size_t)b * ep.sC + (size_t)row * ep.ldc : nullptr;
   const float* Eh = ep.E1_hi ? ep.E1_hi + (size_t)b * ep.sE1 + (size_t)row * ep.lde1 : nullptr;
   const float* El = ep.E1_lo ? ep.E1_lo + (size_t)b * ep.sE1 + (size_t)row * ep.lde1 : nullptr;
+  const int row0 = tm * tc::BM + q * 32;   // first row of this warp
+  float* Cb = ep.C_hi + (size_t)b * ep.sC;
+  float* Clb = ep.C_lo ? ep.C_lo + (size_t)b * ep.sC : nullptr;
 #pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += 32) {
+  for (int c0 = 32 * half; c0 < BN; c0 += 32 * EPI_WARPS / 4) {   // the warps of a quarter interleave the chunks
+    const int colbase = tn * BN + c0;
+    if (colbase >= p.N) break;
     uint32_t v[32], v2[32];
+    const long long e0 = dbg ? clock64() : 0;
+    // interior chunk (the common case): 32 full columns inside the tile and the matrix, 16-byte
+    // aligned rows.  One lean instruction stream per 4-column group; the generic path below
+    // handles ragged edges element by element.
+    // (with one warp per quarter the direct-store path below measured faster than the patch)
+    const bool fast = EPI_WARPS > 4 && c0 + 32 <= BN && colbase + 32 <= p.N && vec_c && (Eh == nullptr || vec_e);
+    if (fast) {
+      tc::tmem_ld32x2(tmem_acc + ((uint32_t)(q * 32) << 16) + c0, BN, v, v2);
+      const long long e1 = dbg ? clock64() : 0;
+      t_ld += e1 - e0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));   // frees v2
+      float4 e[8];
+      if (Eh && row < p.M) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e[j] = *reinterpret_cast<const float4*>(Eh + colbase + 4 * j);
+        if (El) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 l = *reinterpret_cast<const float4*>(El + colbase + 4 * j);
+            e[j].x += l.x; e[j].y += l.y; e[j].z += l.z; e[j].w += l.w;
+          }
+        }
+      }
+      // tcgen05.ld hands every thread 32 consecutive columns of ITS row, so direct stores touch 32
+      // different lines per instruction and the LSU retires one line per cycle (measured: 4096
+      // cycles for a 128 x 128 tile).  Each 32 x 16 half chunk goes through a padded shared-memory
+      // patch instead and leaves as eight 64-byte row segments per instruction.
+      float* mine = stg + lane * EPI_LD;
+      const int cr = lane >> 2, cc = (lane & 3) * 4;   // coalesced pass: rows cr + 8 i, columns cc .. cc + 3
+      const int dcol = row - colbase;                  // this row's diagonal column inside the chunk, if any
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const int j = 4 * hh + j4;
+          float4 o;
+          o.x = alpha * __uint_as_float(v[4 * j + 0]);
+          o.y = alpha * __uint_as_float(v[4 * j + 1]);
+          o.z = alpha * __uint_as_float(v[4 * j + 2]);
+          o.w = alpha * __uint_as_float(v[4 * j + 3]);
+          if (Eh && row < p.M) {
+            o.x = fmaf(beta, e[j].x, o.x); o.y = fmaf(beta, e[j].y, o.y);
+            o.z = fmaf(beta, e[j].z, o.z); o.w = fmaf(beta, e[j].w, o.w);
+          }
+          *reinterpret_cast<float4*>(mine + 4 * j4) = o;
+        }
+        // diagonal term: one read-modify-write of the thread's own patch row (cheaper than a select
+        // per element: the epilogue warps are latency-bound, every instruction counts)
+        if (diag != 0.f && dcol >= 16 * hh && dcol < 16 * hh + 16) mine[dcol - 16 * hh] += diag;
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = cr + 8 * i;
+          if (row0 + r < p.M) {
+            const float4 o = *reinterpret_cast<const float4*>(stg + r * EPI_LD + cc);
+            const size_t off = (size_t)(row0 + r) * ep.ldc + colbase + 16 * hh + cc;
+            if (Clb) {
+              float4 h, l;
+              h.x = tc::rna_tf32(o.x); l.x = o.x - h.x; h.y = tc::rna_tf32(o.y); l.y = o.y - h.y;
+              h.z = tc::rna_tf32(o.z); l.z = o.z - h.z; h.w = tc::rna_tf32(o.w); l.w = o.w - h.w;
+              *reinterpret_cast<float4*>(Cb + off) = h;
+              *reinterpret_cast<float4*>(Clb + off) = l;
+            } else {
+              *reinterpret_cast<float4*>(Cb + off) = o;
+            }
+          }
+        }
+        __syncwarp();
+      }
+      if (dbg) t_rest += clock64() - e1;
+      continue;
+    }
     tc::tmem_ld32x2(tmem_acc + ((uint32_t)(q * 32) << 16) + c0, BN, v, v2);
+    const long long e1 = dbg ? clock64() : 0;
+    t_ld += e1 - e0;
     if (row < p.M) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
@@ -270,7 +362,9 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, const TcEpi&
         }
       }
     }
+    if (dbg) t_rest += clock64() - e1;
   }
+  if (dbg && q == 2 && lane == 0) { dbg[14] = t_ld; dbg[15] = t_rest; }
 }
 
 // the MMAs of one K slab: operand set (Ah | Al | Bh | Bl) OFF bytes behind the slab descriptor d0.
@@ -299,6 +393,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                const __grid_constant__ CUtensorMap tm2Ah, const __grid_constant__ CUtensorMap tm2Al,
                const __grid_constant__ CUtensorMap tm2Bh, const __grid_constant__ CUtensorMap tm2Bl, TcParams p) {
   using C = tc::Cfg<BN>;
+  constexpr int EPI_WARPS = RAW ? tc::EPI_WARPS_RAW : tc::EPI_WARPS_SPLIT;
+  constexpr int ROLE_THREADS = 64 + 32 * EPI_WARPS;   // TMA warp, MMA warp, epilogue warps; the split warps follow
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = tc::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                 // 128B swizzle needs 1024-byte alignment
@@ -329,7 +425,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       tc::tma_prefetch_desc(&tm2Bh); tc::tma_prefetch_desc(&tm2Bl);
     }
     for (int s = 0; s < C::STAGES; ++s) { tc::mbar_init(full_bar(s), 1); tc::mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { tc::mbar_init(tfull_bar(a), 1); tc::mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { tc::mbar_init(tfull_bar(a), 1); tc::mbar_init(tempty_bar(a), EPI_WARPS); }
     if (RAW) for (int s = 0; s < C::STAGES; ++s) tc::mbar_init(split_bar(s), tc::SPLIT_WARPS / 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -417,14 +513,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       }
     }
     __syncwarp();
-  } else if (RAW && warp >= 6) {
+  } else if (RAW && warp >= 2 + EPI_WARPS) {
     // split warps: lo = x - trunc_tf32(x) next to the raw slab (which the tensor core reads as hi).
     // The 128B swizzle permutes 16-byte chunks identically in the hi and lo slots, so the pass is a
     // flat elementwise walk over the raw bytes.
     // Two groups of four warps take alternate slabs, so that the wait -> load -> store -> fence ->
     // arrive latency chain of one slab overlaps the next one's.
     constexpr int NT = 32 * tc::SPLIT_WARPS / 2;
-    const int t = (threadIdx.x - tc::THREADS) % NT, grp = (threadIdx.x - tc::THREADS) / NT;
+    const int t = (threadIdx.x - ROLE_THREADS) % NT, grp = (threadIdx.x - ROLE_THREADS) / NT;
     constexpr int A_CH = tc::A_BYTES / 16, B_CH = C::B_BYTES / 16;   // 16-byte chunks per slab
     const long long my_tiles = total_tiles > (int)blockIdx.x ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const long long nslab = my_tiles * num_kb;
@@ -440,18 +536,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       float4* a_lo = reinterpret_cast<float4*>(sa + tc::A_BYTES);
       const float4* b_hi = reinterpret_cast<const float4*>(sa + 2 * tc::A_BYTES);
       float4* b_lo = reinterpret_cast<float4*>(sa + 2 * tc::A_BYTES + C::B_BYTES);
-      float4 xa[A_CH / NT];
+      // batches of eight 16-byte chunks per thread: enough loads in flight, 32 registers
+      constexpr int BATCH = 8;
 #pragma unroll
-      for (int j = 0; j < A_CH / NT; ++j) xa[j] = a_hi[t + j * NT];
+      for (int j0 = 0; j0 < A_CH / NT; j0 += BATCH) {
+        float4 x[BATCH];
 #pragma unroll
-      for (int j = 0; j < A_CH / NT; ++j) a_lo[t + j * NT] = tc::lo4(xa[j]);
-      float4 xb[(B_CH + NT - 1) / NT];
+        for (int j = 0; j < BATCH; ++j) x[j] = a_hi[t + (j0 + j) * NT];
 #pragma unroll
-      for (int j = 0; j < (B_CH + NT - 1) / NT; ++j)
-        if (B_CH % NT == 0 || t + j * NT < B_CH) xb[j] = b_hi[t + j * NT];
+        for (int j = 0; j < BATCH; ++j) a_lo[t + (j0 + j) * NT] = tc::lo4(x[j]);
+      }
+      constexpr int B_IT = (B_CH + NT - 1) / NT;
 #pragma unroll
-      for (int j = 0; j < (B_CH + NT - 1) / NT; ++j)
-        if (B_CH % NT == 0 || t + j * NT < B_CH) b_lo[t + j * NT] = tc::lo4(xb[j]);
+      for (int j0 = 0; j0 < B_IT; j0 += BATCH) {
+        float4 x[BATCH];
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j)
+          if (j0 + j < B_IT && (B_CH % NT == 0 || t + (j0 + j) * NT < B_CH)) x[j] = b_hi[t + (j0 + j) * NT];
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j)
+          if (j0 + j < B_IT && (B_CH % NT == 0 || t + (j0 + j) * NT < B_CH)) b_lo[t + (j0 + j) * NT] = tc::lo4(x[j]);
+      }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tensor-core (async proxy) reads
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(split_bar(stage));
@@ -469,7 +574,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       tc::mbar_wait(tfull_bar(acc), acc_phase);
       tc::tc_fence_after();
       if (dbg && tile == (int)blockIdx.x && warp == 2 && lane == 0) dbg[5] = clock64();
-      tc_epilogue_tile<BN>(p, ep, tmem_base + acc * C::ACC_STRIDE, tm, tn, b, q, lane);
+      tc_epilogue_tile<BN, EPI_WARPS>(p, ep, tmem_base + acc * C::ACC_STRIDE, tm, tn, b, q, (warp - 2) >> 2, lane,
+                           reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256) + (warp - 2) * 32 * EPI_LD,
+                           tile == (int)blockIdx.x ? dbg : nullptr);
       tc::tc_fence_before();
       __syncwarp();
       if (dbg && tile == (int)blockIdx.x && warp == 2 && lane == 0) dbg[6] = clock64();
