@@ -122,13 +122,22 @@ __global__ void chol_copy_shift_kernel(const float* __restrict__ src, long long 
 static inline size_t al4c(size_t x) { return (x + 3) & ~(size_t)3; }
 static inline int nblocks_c(int D) { return (D + CB - 1) / CB; }
 
-// scratch: Winv [nblk][B][CB][CB] | logdet parts [B][nblk] | fail [B] | Tpanel [B][CB][D]
-size_t chol_scratch_floats(int B, int D) {
-  const size_t nb = nblocks_c(D);
-  return al4c(nb * B * CB * CB) + al4c((size_t)B * nb) + al4c(B) + al4c((size_t)B * CB * D);
+// padded order of the recursive triangular inverse: CB * 2^levels >= D
+static inline int padded_order(int D) {
+  int dp = CB;
+  while (dp < D) dp *= 2;
+  return dp;
 }
 
-struct CholBuf { float* Winv; float* ldpart; int* fail; float* Tp; };
+// scratch: Winv [nblk][B][CB][CB] | logdet parts [B][nblk] | fail [B] | Tpanel [B][CB][D] |
+//          recursive inverse on the tensor pipe: Lp, W, Wt, Tt, each [B][Dp][Dp]
+size_t chol_scratch_floats(int B, int D) {
+  const size_t nb = nblocks_c(D);
+  const size_t dp = padded_order(D);
+  return al4c(nb * B * CB * CB) + al4c((size_t)B * nb) + al4c(B) + al4c((size_t)B * CB * D) + 4 * al4c((size_t)B * dp * dp);
+}
+
+struct CholBuf { float* Winv; float* ldpart; int* fail; float* Tp; float* R[4]; };
 static CholBuf chol_carve(float* scratch, int B, int D) {
   const size_t nb = nblocks_c(D);
   CholBuf c;
@@ -136,6 +145,8 @@ static CholBuf chol_carve(float* scratch, int B, int D) {
   c.ldpart = c.Winv + al4c(nb * B * CB * CB);
   c.fail = reinterpret_cast<int*>(c.ldpart + al4c((size_t)B * nb));
   c.Tp = reinterpret_cast<float*>(c.fail) + al4c(B);
+  const size_t dp = padded_order(D);
+  for (int i = 0; i < 4; ++i) c.R[i] = c.Tp + al4c((size_t)B * CB * D) + (size_t)i * al4c((size_t)B * dp * dp);
   return c;
 }
 
@@ -178,10 +189,97 @@ int chol_factor(float* A, int B, int D, float shift, const float* shift_dev, flo
 }
 const int* chol_fail_flags(float* scratch, int B, int D) { return chol_carve(scratch, B, D).fail; }
 
+
+// ---- triangular inverse by recursive doubling on the tensor pipe -----------------------------------
+// inv([L11 0; L21 L22]) = [W11 0; -W22 L21 W11, W22]: starting from the CB x CB diagonal inverses of
+// chol_diag_kernel, every level doubles the block size with three tcgen05 products per block pair
+// (all pairs of a level in one batched launch when B == 1).  W and its transpose Wt are carried
+// together so that every operand is K-major as stored:
+//   Tt  = Wt11 L21^T   (= (L21 W11)^T)      A = Wt11, B rows = L21 rows
+//   W21 = -W22 T                            A = W22,  B rows = Tt rows
+//   Wt12 = -Tt W22^T   (= W21^T)            A = Tt,   B rows = W22 rows
+// The matrices are padded to Dp = CB 2^levels (zero rows/columns: they never reach the D x D part).
+
+// Lp = lower triangle of the factor, zero elsewhere and in the padding
+__global__ void chol_pad_kernel(const float* __restrict__ Lf, int D, int Dp, float* __restrict__ Lp) {
+  const size_t n = (size_t)Dp * Dp;
+  const float* L = Lf + (size_t)blockIdx.y * D * D;
+  float* out = Lp + (size_t)blockIdx.y * n;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / Dp), j = (int)(idx % Dp);
+    out[idx] = (i < D && j <= i) ? L[(size_t)i * D + j] : 0.f;
+  }
+}
+// W, Wt <- block diagonal of the CB x CB inverses (and their transposes), zero elsewhere
+__global__ void chol_winit2_kernel(const float* __restrict__ Winv, int nblk, int Dp, float* __restrict__ W,
+                                   float* __restrict__ Wt) {
+  const int b = blockIdx.y;
+  const size_t n = (size_t)Dp * Dp;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / Dp), j = (int)(idx % Dp);
+    float v = 0.f, vt = 0.f;
+    if (i / CB == j / CB && i / CB < nblk) {
+      const float* blk = Winv + ((size_t)(i / CB) * gridDim.y + b) * CB * CB;
+      v = blk[(i % CB) * CB + (j % CB)];
+      vt = blk[(j % CB) * CB + (i % CB)];
+    }
+    W[(size_t)b * n + idx] = v;
+    Wt[(size_t)b * n + idx] = vt;
+  }
+}
+
+static TcGemm tri_gemm(const float* A, const float* Bop, float* C, int s, int Dp, long long stride, float alpha) {
+  TcGemm g;
+  g.A_hi = A; g.B_hi = Bop; g.C_hi = C;
+  g.M = g.N = g.K = s;
+  g.lda = g.ldb = g.ldc = Dp;
+  g.sA = g.sB = g.sC = stride;
+  g.alpha = alpha;
+  return g;
+}
+
+static int chol_inverse_tc(const float* Lf, int B, int D, float* Ainv, float alpha, const float* E1, long long sE1,
+                           float beta, const CholBuf& c, cudaStream_t st) {
+  const int Dp = padded_order(D), nb = nblocks_c(D);
+  const long long n2p = (long long)Dp * Dp;
+  float *Lp = c.R[0], *W = c.R[1], *Wt = c.R[2], *Tt = c.R[3];
+  dim3 grid(128, B);
+  chol_pad_kernel<<<grid, 256, 0, st>>>(Lf, D, Dp, Lp);
+  UGLAD_CHECK_LAUNCH("chol_pad_kernel");
+  chol_winit2_kernel<<<grid, 256, 0, st>>>(c.Winv, nb, Dp, W, Wt);
+  UGLAD_CHECK_LAUNCH("chol_winit2_kernel");
+  for (int s = CB; s < Dp; s *= 2) {
+    const int npairs = Dp / (2 * s);
+    // B == 1: all pairs of the level in one batch (stride 2s rows + 2s columns); else one pair per
+    // launch, batched over the graphs
+    const int outer = (B == 1) ? 1 : npairs;
+    const int batch = (B == 1) ? npairs : B;
+    const long long stride = (B == 1) ? 2LL * s * (Dp + 1) : n2p;
+    for (int p = 0; p < outer; ++p) {
+      const size_t o11 = (size_t)(2 * s * p) * (Dp + 1);          // block (2sp, 2sp)
+      const size_t o22 = o11 + (size_t)s * (Dp + 1);               // block (2sp + s, 2sp + s)
+      const size_t o21 = o11 + (size_t)s * Dp;                     // block (2sp + s, 2sp)
+      const size_t o12 = o11 + (size_t)s;                          // block (2sp, 2sp + s)
+      if (launch_tc_gemm(tri_gemm(Wt + o11, Lp + o21, Tt + o12, s, Dp, stride, 1.f), batch, st)) return 1;
+      if (launch_tc_gemm2(tri_gemm(W + o22, Tt + o12, W + o21, s, Dp, stride, -1.f),
+                          tri_gemm(Tt + o12, W + o22, Wt + o12, s, Dp, stride, -1.f), batch, st)) return 1;
+    }
+  }
+  // Ainv = alpha W^T W + beta E1 = alpha Wt Wt^T + beta E1
+  TcGemm g;
+  g.A_hi = Wt; g.B_hi = Wt;
+  g.M = g.N = g.K = D;
+  g.lda = g.ldb = Dp; g.sA = g.sB = n2p;
+  g.alpha = alpha; g.beta = beta; g.E1_hi = E1; g.sE1 = sE1; g.lde1 = D;
+  g.C_hi = Ainv; g.ldc = D; g.sC = (long long)D * D;
+  return launch_tc_gemm(g, B, st);
+}
+
 // Ainv = (L L^T)^-1 from the factor left in Lf by chol_factor (same scratch).  W: [B][D][D] work.
 int chol_inverse(const float* Lf, int B, int D, float* W, float* Ainv, float alpha, const float* E1,
                  long long sE1, float beta, float* scratch, cudaStream_t st) {
   const CholBuf c = chol_carve(scratch, B, D);
+  if (ns_use_tc() && tc_raw_enabled()) return chol_inverse_tc(Lf, B, D, Ainv, alpha, E1, sE1, beta, c, st);
   const int nb = nblocks_c(D);
   const long long n2 = (long long)D * D;
   dim3 grid(64, B);
