@@ -133,22 +133,28 @@ int uglad_profile_read(int kind, double* total_ms, unsigned long long* launches,
  * "eig_keepg" (-1 auto / 0 / 1: keep A + sigma I in a second shared-memory buffer),
  * "small_d_max" (threshold between the eigensolver path and the large-D path, <= 232),
  * "use_tc" (1: tcgen05 3xTF32 products in the large-D path, 0: FP32 SIMT products),
- * "tc_bn" (tile width of the tcgen05 kernel: 0 auto / 64 / 112 / 128).                      */
+ * "tc_bn" (tile width of the tcgen05 kernel: 0 auto / 64 / 112 / 128),
+ * "tc_raw" (1, default: the large-D chain keeps plain FP32 matrices and the tcgen05 kernel forms
+ * hi/lo in shared memory; 0: pre-split hi/lo pairs in HBM), "tc_dual" / "tc_pdl" (pair independent
+ * products into one launch / programmatic dependent launch, both 1 by default).              */
 int uglad_tune(const char* key, int value);
 
-/* developer timeline of the tcgen05 GEMM: buf = device int64[148][8] (NULL switches it off); each
+/* developer timeline of the tcgen05 GEMM: buf = device int64[148][16] (NULL switches it off); each
  * CTA stamps clock64 at {start, setup done, dependency wait done, first operands landed, last MMA
- * committed, accumulator visible to the epilogue, epilogue done} for its first tile.          */
+ * committed, accumulator visible to the epilogue, epilogue done, start (wall clock)} for its first
+ * tile, followed by cycle sums of the MMA thread {wait, issue, commit}, of the split warps {wait,
+ * -, convert} and of one epilogue warp {tcgen05.ld, math + stores}.                           */
 int uglad_tc_debug_buffer(void* buf);
-/* developer benchmark: split the operands once, then `reps` back-to-back launches of the product
- * (split_out: write the hi/lo pair into scratch instead of C).                                */
+/* developer benchmark: `reps` back-to-back launches of the product (operands pre-split once when
+ * "tc_raw" is 0; split_out: write the hi/lo pair into scratch instead of C).                 */
 int uglad_tc_gemm_repeat(const float* A, const float* B, float* C, int M, int N, int K, int batch, int reps,
                          int split_out, float* scratch, void* stream);
 
 /* building blocks exported for the parity tests */
 /* the tcgen05 3xTF32 product of the large-D path on plain operands:
  * C[b] = alpha A[b] B[b]^T + beta E1[b] + diag I, A [batch][M][K], B [batch][N][K], C / E1 [batch][M][N]
- * (E1 may be NULL).  scratch: uglad_tc_gemm_scratch_floats floats (the hi/lo split operands).   */
+ * (E1 may be NULL).  scratch: uglad_tc_gemm_scratch_floats floats (the hi/lo split operands; unused
+ * when "tc_raw" is 1, K % 4 == 0 and the operands are 16-byte aligned: they are then read in place). */
 size_t uglad_tc_gemm_scratch_floats(int M, int N, int K, int batch);
 int uglad_tc_gemm(const float* A, const float* B, const float* E1, float* C, int M, int N, int K, int batch,
                   float alpha, float beta, float diag, float* scratch, void* stream);

@@ -464,6 +464,14 @@ int uglad_glad_backward(const uglad_dims* d, const float* S, const float* params
       float* Ts = ws + w.sp;
       if (launch_tcs_split(ws + w.theta, (long long)D * D, B, D, D, D, w.ldp, Ts, Ts + w.n2p, st)) return 1;
       if (tc_mm(Ts, Ts + w.n2p, Ts, Ts + w.n2p, T1, nullptr, B, D, w.ldp, st)) return 1;
+    } else if (w.large && ns_use_tc() && tc_raw_enabled() && D % 4 == 0) {  // plain operands, split in the kernel
+      TcGemm g;
+      g.A_hi = ws + w.theta; g.B_hi = ws + w.theta;
+      g.M = g.N = g.K = D;
+      g.lda = g.ldb = g.ldc = D;
+      g.sA = g.sB = g.sC = (long long)D * D;
+      g.C_hi = T1;
+      if (launch_tc_gemm(g, B, st)) return 1;
     } else if (bgemm(ws + w.theta, 0, ws + w.theta, 0, T1, B, D, st)) {
       return 1;
     }
