@@ -104,6 +104,15 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// MUFU-based activations of the per-entry rho_l1 MLP (six tanh and one sigmoid per matrix entry: the
+// libm versions made z_update instruction-bound).  Absolute error ~1e-7 (ex2.approx + rcp.approx;
+// tanh(x) = sign(x) (1 - 2 / (e^{2|x|} + 1)) saturates cleanly), two orders below the parity budget.
+__device__ __forceinline__ float fast_tanh(float x) {
+  const float e = __expf(2.f * fabsf(x));
+  const float t = 1.f - __fdividef(2.f, e + 1.f);
+  return copysignf(t, x);
+}
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
 // ---------------------------------------------------------------------------------------
 // Newton-Schulz iteration collapsed onto eigenvalues (torch_sqrtm.py:12-45).
@@ -147,7 +156,7 @@ struct RhoMLP {
     for (int i = 0; i < HM; ++i) {
       if (i < H) {
         const float* r = w + pl.rW1 + i * UGLAD_NF;
-        h1[i] = tanhf(fmaf(r[0], x, fmaf(r[1], s, fmaf(r[2], f, w[pl.rb1 + i]))));
+        h1[i] = fast_tanh(fmaf(r[0], x, fmaf(r[1], s, fmaf(r[2], f, w[pl.rb1 + i]))));
       }
     }
 #pragma unroll
@@ -157,14 +166,14 @@ struct RhoMLP {
 #pragma unroll
         for (int j = 0; j < HM; ++j)
           if (j < H) a = fmaf(w[pl.rW2 + i * H + j], h1[j], a);
-        h2[i] = tanhf(a);
+        h2[i] = fast_tanh(a);
       }
     }
     float o = w[pl.rb3];
 #pragma unroll
     for (int j = 0; j < HM; ++j)
       if (j < H) o = fmaf(w[pl.rW3 + j], h2[j], o);
-    return sigmoidf_(o);
+    return fast_sigmoid(o);
   }
 };
 
