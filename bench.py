@@ -162,7 +162,7 @@ def run_reference(args, wl, rank, world):
 KERNELS = ((0, "eig_jacobi_small_kernel"), (1, "tc_gemm_kernel"))
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
 # (profiles/r01_ncu_full_*.txt), keyed by (kernel, graphs, D); bytes
-NCU_TRAFFIC = {("eig", 256, 100): 30.8e6, ("tc", 1, 1000): 16.1e6}
+NCU_TRAFFIC = {("eig", 256, 100): 30.8e6, ("tc", 1, 1000): 10.7e6}   # tc: r01_ncu_full_tc_gemm_d1000_v3.txt (8-12 MB)
 
 
 def time_gpu_workload(name, steps, warmup, rank, world, group, dev, profile=False):
@@ -266,15 +266,15 @@ def roofline_of(r, peaks):
         if not peak:
             peak, src = 1400.0, "fallback (B200_PROFILING.md sustained bf16)"
         achieved = tcg["work"] / (tcg["ms"] * 1e-3) / 1e12
-        return {"bound": "tensor", "kernel": "tc_gemm_kernel (tcgen05.mma kind::tf32, 3xTF32 split operands)",
+        return {"bound": "tensor", "kernel": "tc_gemm_kernel (tcgen05.mma kind::tf32, 3xTF32: hi/lo operands, two MMAs per K granule)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": NCU_TRAFFIC.get(("tc", r["B"], r["D"])),
                 "peak_source": src, "avg_launch_ms": tcg["ms"] / tcg["launches"],
                 "launches_per_step": tcg["launches"] / prof["steps"], "kernel_share_of_step": tcg["ms"] / step_ms,
                 "tf32_pipe_frac": 3.0 * achieved / (peak / 2.0),
-                "note": "achieved counts the algorithmic 2MNK flops per product; every product issues three "
-                        "TF32 MMAs and the TF32 pipe peaks at half the bf16 rate, so the tensor pipe itself "
-                        "runs at tf32_pipe_frac of its own peak"}
+                "note": "achieved counts the algorithmic 2MNK flops per product; every product costs three "
+                        "TF32 passes (hi*hi, hi*lo, lo*hi) and the TF32 pipe peaks at half the bf16 rate, so the "
+                        "tensor pipe itself runs at tf32_pipe_frac of its own peak"}
     peak = peaks.get("hbm_gbs")
     src = "measured (MEASURED_PEAKS.json hbm_gbs)"
     if not peak:

@@ -1,31 +1,39 @@
 // Batched 3xTF32 GEMM on the 5th-generation tensor cores (sm_100a): C = epi(A * B^T).
 //
-// Every operand is a "split" matrix: two FP32 arrays hi + lo with hi = tf32(x) (low 13 mantissa
-// bits zero) and lo = x - hi (exact), so x = hi + lo carries full FP32 precision and
-//   A B^T  ~=  A_hi B_hi^T + A_lo B_hi^T + A_hi B_lo^T          (error ~2^-21 |A||B|, FP32 accumulate)
+// Every operand is used as hi + lo with hi a TF32 number and lo = x - hi (exact), so x = hi + lo
+// carries full FP32 precision and
+//   A B^T  ~=  A_hi B_hi^T + A_hi B_lo^T + A_lo B_hi^T          (error ~2^-21 |A||B|, FP32 accumulate)
 // which is what the 1e-4 parity budget on theta after 15 unrolled layers needs (single-pass TF32
 // is 1e-3).  Both operands are K-major (row-major [rows][K]); the callers only ever multiply by
 // symmetric matrices or provide the transpose explicitly, so B^T costs nothing.
 //
-// Structure (persistent, warp-specialised, one CTA per SM):
-//   warp 0   : TMA producer -- cp.async.bulk.tensor.3d of the four 32-float-wide K slabs
-//              (A_hi, A_lo: 128 rows; B_hi, B_lo: BN rows), 128B swizzle, mbarrier complete_tx
-//   warp 1   : MMA issuer   -- one lane issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8), three
-//              operand pairings per K granule, accumulating in TMEM; tcgen05.commit frees the slab
-//   warps 2-5: epilogue     -- tcgen05.ld of the accumulator (two TMEM stages, so the next tile's
-//              MMAs overlap), alpha/beta/diag epilogue, hi/lo split, vectorised stores
-// Raw-operand mode (RAW = true; operands with lo == nullptr; the default of the Newton-Schulz chain):
-// the operands are plain FP32 matrices.  TMA brings ONE 4-byte word per element into the hi slot
-// of the stage; the tensor core reads a 32-bit container as TF32 by dropping the low 13 mantissa
-// bits, so the raw word IS the hi operand (hi = trunc(x)), and eight more warps (6-13) only write
-// lo = x - trunc(x) (exact) into the neighbouring slot behind a generic->async proxy fence.  Half
-// the L2->SM bytes, and every producer of the chain writes 4 instead of 8 bytes per element.
 // Two MMAs per K granule instead of three: B_hi and B_lo sit next to each other in the stage, so
 //   acc[:, 0:2BN] += A_hi * [B_hi ; B_lo]^T   (one instruction, N = 2 BN)
 //   acc[:, 0:BN]  += A_lo * B_hi^T
 // and the epilogue adds the two column halves.  A K = 8 TF32 instruction with both operands in
 // shared memory is bound by the 4 KB A-operand read (~65-78 cycles measured for N = 64 ... 128), so
 // the wide instruction costs no more than a narrow one until N/2 cycles of tensor work exceed it.
+//
+// Operand forms:
+//   pre-split (RAW = false): hi = tf32(x) (round to nearest) and lo are two FP32 arrays written by the
+//              producer (eigenvector products of the D <= 166 path); TMA loads all four slabs.
+//   raw (RAW = true; lo == nullptr; the Newton-Schulz chain and the Cholesky helpers): plain FP32
+//              matrices.  TMA brings ONE 4-byte word per element into the hi slot; the tensor core
+//              reads a 32-bit container as TF32 by dropping the low 13 mantissa bits, so the raw
+//              word IS the hi operand (hi = trunc(x)), and eight split warps only write
+//              lo = x - trunc(x) (exact) into the neighbouring slot behind fence.proxy.async.  Half
+//              the L2->SM bytes, and every producer of the chain writes 4 bytes per element.
+//
+// Structure (persistent, warp-specialised, one CTA per SM):
+//   warp 0       : TMA producer -- cp.async.bulk.tensor.3d of the 32-float-wide K slabs (A: 128 rows,
+//                  B: BN rows), 128B swizzle, mbarrier complete_tx, 3-4 stages
+//   warp 1       : MMA issuer   -- one elected lane (elect.sync: no per-instruction election loops)
+//                  issues tcgen05.mma.kind::tf32 (M = 128, K = 8) with base + immediate descriptors,
+//                  accumulating in TMEM; tcgen05.commit frees the slab
+//   epilogue     : 8 warps (pre-split) / 4 warps (raw) -- tcgen05.ld of the accumulator (two TMEM
+//                  stages, so the next tile's MMAs overlap), alpha/beta/diag epilogue, optional
+//                  hi/lo split output; the 8-warp form coalesces its stores through a shared-memory patch
+//   split (raw)  : 8 warps in two groups taking alternate slabs
 // A launch carries one product or two independent products of the same shape (two sets of tensor
 // maps and epilogue parameters): the second doubles the tiles the persistent grid can spread over
 // 148 SMs.  Launches are chained with programmatic dependent launch: the prologue (barriers, TMEM
