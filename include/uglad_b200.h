@@ -48,6 +48,11 @@ size_t uglad_param_count(int H);
  * X[B][M][D] samples -> S[B][D][D] = (X-mean)^T (X-mean) / M.  mean_out[B][D] is required
  * (it is also the kernel's scratch). */
 int uglad_covariance(const float* X, int B, int M, int D, float* S, float* mean_out, void* stream);
+/* the same covariance with the contraction on the tensor pipe (tcgen05 3xTF32 on the centred,
+ * feature-major samples staged in scratch: uglad_covariance_scratch_floats floats); scratch == NULL
+ * or uglad_tune("use_tc", 0) selects the FP32 kernel of uglad_covariance.                        */
+size_t uglad_covariance_scratch_floats(int B, int M, int D);
+int uglad_covariance_ws(const float* X, int B, int M, int D, float* S, float* mean_out, float* scratch, void* stream);
 
 /* symmetric eigensolver used by every stage.  shift_mode 0: A is positive definite (high
  * relative accuracy, eigenvalues returned as column norms); 1: A is symmetric indefinite.

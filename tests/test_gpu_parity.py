@@ -91,8 +91,17 @@ def test_covariance(dev, B, M, D):
     from uglad_b200 import ops
     rng = np.random.default_rng(M)
     X = rng.random((B, M, D))
-    S = ops.covariance(torch.tensor(X, dtype=torch.float32, device=dev)).cpu().numpy()
+    Xd = torch.tensor(X, dtype=torch.float32, device=dev)
+    S = ops.covariance(Xd).cpu().numpy()   # tcgen05 3xTF32 contraction on the centred, feature-major samples
     assert rel(S, O.covariance(X, offset=0.1)) < 5e-6
+    assert np.array_equal(S, S.transpose(0, 2, 1))   # exactly symmetric
+    ops.tune("use_tc", 0)                   # FP32 SIMT contraction
+    try:
+        S_simt = ops.covariance(Xd).cpu().numpy()
+    finally:
+        ops.tune("use_tc", 1)
+    assert rel(S_simt, O.covariance(X, offset=0.1)) < 5e-6
+    assert rel(S, S_simt) < 5e-6
 
 
 def test_rank_deficient_covariance_is_repaired(dev):

@@ -26,6 +26,8 @@ SIGNATURES = {
     "uglad_last_error": (C.c_char_p, []),
     "uglad_param_count": (_Z, [_I]),
     "uglad_covariance": (_I, [_P, _I, _I, _I, _P, _P, _P]),
+    "uglad_covariance_scratch_floats": (_Z, [_I, _I, _I]),
+    "uglad_covariance_ws": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "uglad_eigh_scratch_floats": (_Z, [_I, _I]),
     "uglad_eigh": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P]),
     "uglad_condition_covariance": (_I, [_P, _I, _I, _F, _P, _P, _P, _P, _P]),

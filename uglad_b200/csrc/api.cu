@@ -207,6 +207,36 @@ int uglad_covariance(const float* X, int B, int M, int D, float* S, float* mean_
   return launch_gemm(g, B, st);
 }
 
+// covariance on the tensor pipe: centre + transpose the samples into K chunks of COV_KC samples
+// ([B][nch][D][COV_KC] in scratch), one batched tcgen05 3xTF32 product Xt_c Xt_c^T / M per (graph,
+// chunk), partials [B][nch][D][D] summed and symmetrised.  Falls back to the FP32 SIMT kernel behind
+// uglad_tune("use_tc", 0).
+constexpr int COV_KC = 128;
+size_t uglad_covariance_scratch_floats(int B, int M, int D) {
+  if (B <= 0 || M <= 0 || D <= 0) return 0;
+  const size_t nch = ((size_t)M + COV_KC - 1) / COV_KC;
+  return al4((size_t)B * nch * D * COV_KC) + al4((size_t)B * nch * D * D);
+}
+int uglad_covariance_ws(const float* X, int B, int M, int D, float* S, float* mean_out, float* scratch, void* stream) {
+  if (!scratch || !ns_use_tc() || !tc_raw_enabled()) return uglad_covariance(X, B, M, D, S, mean_out, stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!X || !S || !mean_out || B <= 0 || M <= 0 || D <= 0) { set_error("covariance: bad arguments"); return 1; }
+  const int nch = (M + COV_KC - 1) / COV_KC;
+  float* Xt = scratch;
+  float* part = scratch + al4((size_t)B * nch * D * COV_KC);
+  if (launch_colmean(X, B, M, D, mean_out, st)) return 1;
+  if (launch_center_transpose(X, mean_out, B, M, D, COV_KC, nch, Xt, st)) return 1;
+  TcGemm g;
+  g.A_hi = Xt; g.B_hi = Xt;
+  g.M = g.N = D; g.K = COV_KC;
+  g.lda = g.ldb = COV_KC;
+  g.sA = g.sB = (long long)D * COV_KC;
+  g.alpha = 1.0f / (float)M;
+  g.C_hi = part; g.ldc = D; g.sC = (long long)D * D;
+  if (launch_tc_gemm(g, B * nch, st)) return 1;
+  return launch_cov_reduce(part, B, nch, D, S, st);
+}
+
 size_t uglad_eigh_scratch_floats(int B, int D) { return eig_scratch_floats(B, D); }
 
 int uglad_eigh_warm(const float* A, int B, int D, int shift_mode, float* w, float* Vt, float* info,

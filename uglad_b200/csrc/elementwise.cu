@@ -582,6 +582,76 @@ int launch_colmean(const float* X, int B, int M, int D, float* mean, cudaStream_
   return 0;
 }
 
+// Centred samples, feature-major and cut into K chunks of `kc` samples:
+//   Xt[(b * nch + c)][d][k] = X[b][c * kc + k][d] - mean[b][d]      (zero beyond the last sample)
+// so that the covariance is a batch of K-major products Xt_c Xt_c^T on the tensor pipe.  The chunks
+// bound the tensor core's truncating accumulation (a sum of squares loses ~half an ulp per
+// accumulated MMA: -6e-6 relative at K = 500 in one accumulator, -1.5e-6 at K = 128); the partial
+// products are summed in FP32 with rounding.  32 x 32 tiles, block (32, 8); kc is a multiple of 32.
+__global__ void center_transpose_kernel(const float* __restrict__ X, const float* __restrict__ mean, int M, int D,
+                                        int kc, int nch, float* __restrict__ Xt) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z, m0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  const float* Xb = X + (size_t)b * M * D;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int m = m0 + r, d = d0 + threadIdx.x;
+    t[r][threadIdx.x] = (m < M && d < D) ? Xb[(size_t)m * D + d] - mean[(size_t)b * D + d] : 0.f;
+  }
+  __syncthreads();
+  const int c = m0 / kc, k0 = m0 - c * kc;   // a 32-sample tile never straddles two chunks
+  float* Tb = Xt + ((size_t)b * nch + c) * D * kc;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int d = d0 + r;
+    if (d < D) Tb[(size_t)d * kc + k0 + threadIdx.x] = t[threadIdx.x][r];
+  }
+}
+int launch_center_transpose(const float* X, const float* mean, int B, int M, int D, int kc, int nch, float* Xt,
+                            cudaStream_t st) {
+  dim3 grid(nch * (kc / 32), (D + 31) / 32, B), blk(32, 8);
+  center_transpose_kernel<<<grid, blk, 0, st>>>(X, mean, M, D, kc, nch, Xt);
+  UGLAD_CHECK_LAUNCH("center_transpose_kernel");
+  return 0;
+}
+// S[b] = sum_c (P[b][c] + P[b][c]^T) / 2: the chunk partials summed and made exactly symmetric (the
+// tensor-pipe product groups its hi/lo terms differently for (i, j) and (j, i)).  One block per pair
+// of mirrored 32 x 32 tiles.
+__global__ void cov_reduce_kernel(const float* __restrict__ P, int nch, int D, float* __restrict__ S) {
+  if (blockIdx.x > blockIdx.y) return;
+  __shared__ float ta[32][33], tb[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  const size_t n2 = (size_t)D * D;
+  const float* Pb = P + (size_t)blockIdx.z * nch * n2;
+  float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = 0; c < nch; ++c) {
+    const float* Pc = Pb + (size_t)c * n2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = threadIdx.y + 8 * i, cc = threadIdx.x;
+      if (bx + r < D && by + cc < D) sa[i] += Pc[(size_t)(bx + r) * D + by + cc];   // tile (bx, by)
+      if (by + r < D && bx + cc < D) sb[i] += Pc[(size_t)(by + r) * D + bx + cc];   // tile (by, bx)
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    ta[threadIdx.y + 8 * i][threadIdx.x] = sa[i];
+    tb[threadIdx.y + 8 * i][threadIdx.x] = sb[i];
+  }
+  __syncthreads();
+  float* Sb = S + (size_t)blockIdx.z * n2;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int c = threadIdx.x;
+    if (bx + r < D && by + c < D) Sb[(size_t)(bx + r) * D + by + c] = 0.5f * (ta[r][c] + tb[c][r]);
+    if (blockIdx.x != blockIdx.y && by + r < D && bx + c < D) Sb[(size_t)(by + r) * D + bx + c] = 0.5f * (tb[r][c] + ta[c][r]);
+  }
+}
+int launch_cov_reduce(const float* P, int B, int nch, int D, float* S, cudaStream_t st) {
+  const int nt = (D + 31) / 32;
+  dim3 grid(nt, nt, B), blk(32, 8);
+  cov_reduce_kernel<<<grid, blk, 0, st>>>(P, nch, D, S);
+  UGLAD_CHECK_LAUNCH("cov_reduce_kernel");
+  return 0;
+}
+
 // prepare_data.py:348-350: if min eig <= 1e-6, S += (offset - min) I (and the eigenvalues move
 // by the same amount, the eigenvectors do not).  One block per graph.
 __global__ void condition_kernel(float* S, float* wS, int D, float offset) {

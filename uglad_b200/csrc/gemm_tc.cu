@@ -533,11 +533,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     const long long my_tiles = total_tiles > (int)blockIdx.x ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const long long nslab = my_tiles * num_kb;
     long long tw = 0, tcv = 0;
-    for (long long i = grp; i < nslab; i += 2) {
+    // Every group waits for EVERY slab in order, also the ones the other group splits: a parity
+    // wait only distinguishes "this phase" from "the previous one", so a group that skipped a
+    // completion of a stage barrier (three stages, two groups: the groups alternate on each stage)
+    // would take the stale completion for the one it is waiting for as soon as the TMA loads of
+    // two stages land out of order -- premature splits of a slab that has not arrived, then a hang.
+    for (long long i = 0; i < nslab; ++i) {
       const int stage = (int)(i % C::STAGES);
       const uint32_t phase = (uint32_t)((i / C::STAGES) & 1);
       const long long c0 = dbg ? clock64() : 0;
       tc::mbar_wait(full_bar(stage), phase);
+      if ((int)(i & 1) != grp) continue;
       const long long c1 = dbg ? clock64() : 0;
       uint8_t* sa = smem + stage * C::STAGE_BYTES;
       const float4* a_hi = reinterpret_cast<const float4*>(sa);

@@ -162,6 +162,9 @@ int launch_loss_terms(const float* theta, const float* S, long long strideS, con
                       int B, int D, float Bdiv, float* part, float* lossb, float* loss_out, unsigned* counter,
                       cudaStream_t st);
 int launch_colmean(const float* X, int B, int M, int D, float* mean, cudaStream_t st);
+int launch_center_transpose(const float* X, const float* mean, int B, int M, int D, int kc, int nch, float* Xt,
+                            cudaStream_t st);
+int launch_cov_reduce(const float* P, int B, int nch, int D, float* S, cudaStream_t st);
 int launch_condition(float* S, float* wS, int B, int D, float offset, cudaStream_t st);
 
 }  // namespace uglad

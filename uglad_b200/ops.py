@@ -36,7 +36,10 @@ def covariance(X: torch.Tensor) -> torch.Tensor:
     B, M, D = X.shape
     S = torch.empty(B, D, D, device=X.device, dtype=torch.float32)
     mean = torch.empty(B, D, device=X.device, dtype=torch.float32)
-    check(_lib.load().uglad_covariance(_ptr(X), B, M, D, _ptr(S), _ptr(mean), _stream(X)), "uglad_covariance")
+    lib = _lib.load()
+    # the contraction runs on the tensor pipe (tcgen05 3xTF32) from centred, feature-major samples in scratch
+    scratch = torch.empty(max(lib.uglad_covariance_scratch_floats(B, M, D), 1), device=X.device, dtype=torch.float32)
+    check(lib.uglad_covariance_ws(_ptr(X), B, M, D, _ptr(S), _ptr(mean), _ptr(scratch), _stream(X)), "uglad_covariance_ws")
     return S
 
 

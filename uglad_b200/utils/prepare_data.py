@@ -85,6 +85,7 @@ class CovariancePrefetcher:
         slots = []
         for _ in range(self.SLOTS):
             sl = {"X": torch.empty(B, M, D, **f), "S": torch.empty(B, D, D, **f), "mean": torch.empty(B, D, **f),
+                  "Xt": torch.empty(max(lib.uglad_covariance_scratch_floats(B, M, D), 1), **f),
                   "scratch": torch.empty(max(lib.uglad_condition_scratch_floats(B, D), 1), **f),
                   "ev": torch.cuda.Event()}
             cc = ops.ConditionedCovariance.__new__(ops.ConditionedCovariance)
@@ -113,7 +114,8 @@ class CovariancePrefetcher:
         with torch.cuda.stream(self.stream):
             st = C.c_void_p(self.stream.cuda_stream)
             sl["X"].copy_(X_host, non_blocking=True)
-            ops.check(lib.uglad_covariance(P(sl["X"]), B, M, D, P(sl["S"]), P(sl["mean"]), st), "uglad_covariance")
+            ops.check(lib.uglad_covariance_ws(P(sl["X"]), B, M, D, P(sl["S"]), P(sl["mean"]), P(sl["Xt"]), st),
+                      "uglad_covariance_ws")
             cc = sl["cc"]
             wV, ww = (prev.VtS, prev.wS) if (prev is not None and prev.VtS is not None) else (None, None)
             ops.check(lib.uglad_condition_covariance_warm(P(sl["S"]), B, D, self.offset, P(cc.wS), P(cc.VtS),
