@@ -350,6 +350,31 @@ def test_tcgen05_3xtf32_gemm(dev, M, N, K, batch, bn, raw):
         ops.tune("tc_raw", 1)
 
 
+def test_tcgen05_gemm_many_tiles_cold_operands(dev):
+    """Regression: ~14 short-K tiles per CTA of the raw-operand kernel (three stages, two split
+    groups) with operand sets rotating through more memory than L2 holds, so that the TMA loads of
+    different stages complete out of order.  A split group that skipped the other group's
+    completions used to mistake a stale barrier phase for its own (hang behind the watchdog trap)."""
+    import ctypes as C
+    from uglad_b200 import _lib, ops
+    lib = _lib.load()
+    M, N, K, batch = 100, 100, 128, 2048
+    g = torch.Generator(device=dev).manual_seed(5)
+    sets = [torch.randn(batch, M, K, device=dev, generator=g) for _ in range(3)]
+    outs = [torch.empty(batch, M, N, device=dev) for _ in range(3)]
+    scratch = torch.empty(max(lib.uglad_tc_gemm_scratch_floats(M, N, K, batch), 1), device=dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for it in range(45):
+        A, out = sets[it % 3], outs[it % 3]
+        rc = lib.uglad_tc_gemm(A.data_ptr(), A.data_ptr(), None, out.data_ptr(), M, N, K, batch, 1.0, 0.0, 0.0,
+                               scratch.data_ptr(), st)
+        assert rc == 0, lib.uglad_last_error().decode()
+    torch.cuda.synchronize()
+    for A, out in zip(sets, outs):
+        ref = torch.einsum("bmk,bnk->bmn", A[:64].double(), A[:64].double())
+        assert (out[:64].double() - ref).abs().max().item() < 2e-3
+
+
 @pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
 def test_large_path_forward_backward_against_reference_golden(dev, force_large_path, path):
     from uglad_b200 import main as ug
