@@ -314,7 +314,7 @@ def force_large_path(request):
     (128, 128, 32, 1, 0), (100, 100, 100, 3, 0), (7, 5, 3, 2, 0), (200, 200, 200, 2, 0), (130, 70, 45, 2, 64),
     (300, 260, 129, 1, 112), (256, 256, 256, 1, 128), (1000, 1000, 1000, 1, 0), (100, 100, 100, 300, 0),
     (300, 260, 132, 1, 112), (130, 70, 44, 2, 64), (129, 250, 520, 2, 128)])
-@pytest.mark.parametrize("raw", [1, 0], ids=["raw", "presplit"])
+@pytest.mark.parametrize("raw", [1, 2, 0], ids=["raw-tma-store", "raw-direct-store", "presplit"])
 def test_tcgen05_3xtf32_gemm(dev, M, N, K, batch, bn, raw):
     """C = alpha A B^T + beta E1 + diag I on the tensor pipe against float64 numpy: FP32-class
     accuracy (3xTF32), ragged edges, batches larger than the SM count, every tile width; plain
@@ -323,7 +323,8 @@ def test_tcgen05_3xtf32_gemm(dev, M, N, K, batch, bn, raw):
     from uglad_b200 import _lib, ops
     lib = _lib.load()
     ops.tune("tc_bn", bn)
-    ops.tune("tc_raw", raw)
+    ops.tune("tc_raw", 1 if raw else 0)
+    ops.tune("tc_tma_store", 1 if raw == 1 else 0)
     try:
         rng = np.random.default_rng(M * 7 + N)
         A = rng.standard_normal((batch, M, K)).astype(np.float32)
@@ -348,6 +349,7 @@ def test_tcgen05_3xtf32_gemm(dev, M, N, K, batch, bn, raw):
     finally:
         ops.tune("tc_bn", 0)
         ops.tune("tc_raw", 1)
+        ops.tune("tc_tma_store", 1)
 
 
 def test_tcgen05_gemm_many_tiles_cold_operands(dev):

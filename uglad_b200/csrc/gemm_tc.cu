@@ -109,6 +109,17 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// one [32 cols x 128 rows] box from shared memory (128B swizzle) to global; rows/columns beyond the
+// tensor are clipped by the TMA unit
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
@@ -178,6 +189,10 @@ struct Cfg {
   static constexpr int ACC_STRIDE = TMEM_COLS / 2;
   static constexpr int EPI_BYTES = EPI_WARPS_SPLIT * 32 * 20 * 4;   // one 32 x 20 float patch per epilogue warp
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + EPI_BYTES;
+  // raw kernel: two 128 x 32 float staging tiles (128B swizzle, 1024-byte aligned) for the TMA stores of C
+  static constexpr int CST_BYTES = 2 * BM * 128;
+  static constexpr int SMEM_RAW = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 1024 /*barriers*/ + CST_BYTES;
+  static_assert(SMEM_RAW <= 232448, "raw-operand kernel exceeds 227 KB of shared memory");
   static constexpr int RAW_TX_BYTES = A_BYTES + B_BYTES;   // raw mode: one word per element arrives by TMA
   // kind::tf32, FP32 accumulate, K-major A and B, M = 128, N = BN
   static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -203,6 +218,7 @@ struct TcParams {
   int M, N, K, batch, tiles_m, tiles_n;
   int nprob;        // 1, or 2: two independent products of the same shape share one launch
   int exp;          // developer experiment (wrong results): 1 = pre-split kernel skips its TMA loads
+  int tma_c[2];     // raw kernel: C of problem i leaves through TMA stores (plain output, 16-byte aligned rows)
   TcEpi e[2];
 };
 
@@ -375,6 +391,111 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& p, const TcEpi&
   if (dbg && q == 2 && lane == 0) { dbg[14] = t_ld; dbg[15] = t_rest; }
 }
 
+// Epilogue of the raw-operand kernel through TMA stores: tcgen05.ld hands every thread 32 consecutive
+// columns of ITS row, and direct stores then touch 32 different lines per instruction (the LSU
+// retires about one line per cycle: 4096 cycles for a 128 x 128 tile, as long as a short-K main
+// loop).  The four epilogue warps instead write each 128 x 32 chunk into a 128B-swizzled staging tile
+// (conflict-free 16-byte row writes) and one thread hands it to the TMA unit, which writes full
+// lines asynchronously and clips the ragged edges; two staging tiles alternate.  The trailing partial
+// chunk (BN = 112: 16 columns) goes through a second, dense 16-column box.  Plain FP32 output and
+// addend only (the host checks).
+template <int BN>
+__device__ __forceinline__ void tc_epilogue_tile_tma(const TcParams& p, const TcEpi& ep, const CUtensorMap* mC,
+                                                     const CUtensorMap* mCp, uint32_t tmem_acc, int tm, int tn, int b, int q, int lane,
+                                                     uint8_t* cst, uint32_t cst_s, int& buf, bool leader) {
+  const int rit = q * 32 + lane;                    // row inside the tile
+  const int row = tm * tc::BM + rit;
+  const float alpha = ep.alpha_dev ? ep.alpha * ep.alpha_dev[b] : ep.alpha;
+  const float beta = ep.beta, diag = ep.diag;
+  const float* Eh = ep.E1_hi ? ep.E1_hi + (size_t)b * ep.sE1 + (size_t)row * ep.lde1 : nullptr;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    const int colbase = tn * BN + c0;
+    if (colbase >= p.N) break;                       // uniform
+    uint32_t v[32], v2[32];
+    tc::tmem_ld32x2(tmem_acc + ((uint32_t)(q * 32) << 16) + c0, BN, v, v2);
+    const bool full = c0 + 32 <= BN;                 // uniform
+    const int dcol = row - colbase;                  // this row's diagonal column inside the chunk, if any
+    if (full) {
+      float4 o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[j].x = alpha * (__uint_as_float(v[4 * j + 0]) + __uint_as_float(v2[4 * j + 0]));
+        o[j].y = alpha * (__uint_as_float(v[4 * j + 1]) + __uint_as_float(v2[4 * j + 1]));
+        o[j].z = alpha * (__uint_as_float(v[4 * j + 2]) + __uint_as_float(v2[4 * j + 2]));
+        o[j].w = alpha * (__uint_as_float(v[4 * j + 3]) + __uint_as_float(v2[4 * j + 3]));
+      }
+      if (Eh && row < p.M) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int col = colbase + 4 * j;
+          if (col + 3 < p.N) {
+            const float4 e = *reinterpret_cast<const float4*>(Eh + col);
+            o[j].x = fmaf(beta, e.x, o[j].x); o[j].y = fmaf(beta, e.y, o[j].y);
+            o[j].z = fmaf(beta, e.z, o[j].z); o[j].w = fmaf(beta, e.w, o[j].w);
+          } else {
+            if (col < p.N) o[j].x = fmaf(beta, Eh[col], o[j].x);
+            if (col + 1 < p.N) o[j].y = fmaf(beta, Eh[col + 1], o[j].y);
+            if (col + 2 < p.N) o[j].z = fmaf(beta, Eh[col + 2], o[j].z);
+          }
+        }
+      }
+      if (leader) tc::tma_store_wait_read<1>();      // the store that read this staging tile two chunks ago is done
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      uint8_t* mine = cst + buf * (tc::BM * 128) + rit * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(mine + ((j ^ (rit & 7)) << 4)) = o[j];
+      if (diag != 0.f && dcol >= 0 && dcol < 32)     // diagonal term: one read-modify-write of the own row
+        *reinterpret_cast<float*>(mine + ((((dcol >> 2) ^ (rit & 7)) << 4) | ((dcol & 3) << 2))) += diag;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> TMA (async proxy) reads
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (leader) {
+        tc::tma_store_3d(mC, cst_s + buf * (tc::BM * 128), colbase, tm * tc::BM, b);
+        tc::tma_store_commit();
+      }
+      buf ^= 1;
+    } else {                                         // trailing partial chunk (BN % 32 columns): dense unswizzled box
+      constexpr int W = BN % 32 ? BN % 32 : 32;
+      float4 o[W / 4];
+#pragma unroll
+      for (int j = 0; j < W / 4; ++j) {
+        o[j].x = alpha * (__uint_as_float(v[4 * j + 0]) + __uint_as_float(v2[4 * j + 0]));
+        o[j].y = alpha * (__uint_as_float(v[4 * j + 1]) + __uint_as_float(v2[4 * j + 1]));
+        o[j].z = alpha * (__uint_as_float(v[4 * j + 2]) + __uint_as_float(v2[4 * j + 2]));
+        o[j].w = alpha * (__uint_as_float(v[4 * j + 3]) + __uint_as_float(v2[4 * j + 3]));
+      }
+      if (Eh && row < p.M) {
+#pragma unroll
+        for (int j = 0; j < W / 4; ++j) {
+          const int col = colbase + 4 * j;
+          if (col + 3 < p.N) {
+            const float4 e = *reinterpret_cast<const float4*>(Eh + col);
+            o[j].x = fmaf(beta, e.x, o[j].x); o[j].y = fmaf(beta, e.y, o[j].y);
+            o[j].z = fmaf(beta, e.z, o[j].z); o[j].w = fmaf(beta, e.w, o[j].w);
+          } else {
+            if (col < p.N) o[j].x = fmaf(beta, Eh[col], o[j].x);
+            if (col + 1 < p.N) o[j].y = fmaf(beta, Eh[col + 1], o[j].y);
+            if (col + 2 < p.N) o[j].z = fmaf(beta, Eh[col + 2], o[j].z);
+          }
+        }
+      }
+      if (leader) tc::tma_store_wait_read<1>();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      uint8_t* mine = cst + buf * (tc::BM * 128) + rit * (W * 4);
+#pragma unroll
+      for (int j = 0; j < W / 4; ++j) *reinterpret_cast<float4*>(mine + (j << 4)) = o[j];
+      if (diag != 0.f && dcol >= 0 && dcol < W) *reinterpret_cast<float*>(mine + (dcol << 2)) += diag;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (leader) {
+        tc::tma_store_3d(mCp, cst_s + buf * (tc::BM * 128), colbase, tm * tc::BM, b);
+        tc::tma_store_commit();
+      }
+      buf ^= 1;
+    }
+  }
+}
+
 // the MMAs of one K slab: operand set (Ah | Al | Bh | Bl) OFF bytes behind the slab descriptor d0.
 // OFF is a compile-time constant, so every descriptor is d0 + immediate (the 14-bit address field
 // cannot carry: shared-memory addresses stay below 256 KB).
@@ -399,7 +520,9 @@ __global__ void __launch_bounds__(RAW ? tc::THREADS_RAW : tc::THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                const __grid_constant__ CUtensorMap tm2Ah, const __grid_constant__ CUtensorMap tm2Al,
-               const __grid_constant__ CUtensorMap tm2Bh, const __grid_constant__ CUtensorMap tm2Bl, TcParams p) {
+               const __grid_constant__ CUtensorMap tm2Bh, const __grid_constant__ CUtensorMap tm2Bl,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tm2C,
+               const __grid_constant__ CUtensorMap tmCp, const __grid_constant__ CUtensorMap tm2Cp, TcParams p) {
   using C = tc::Cfg<BN>;
   constexpr int EPI_WARPS = RAW ? tc::EPI_WARPS_RAW : tc::EPI_WARPS_SPLIT;
   constexpr int ROLE_THREADS = 64 + 32 * EPI_WARPS;   // TMA warp, MMA warp, epilogue warps; the split warps follow
@@ -580,6 +703,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   } else {
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     int acc = 0; uint32_t acc_phase = 0;
+    int cbuf = 0;            // staging tile of the next TMA store (raw kernel)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int b = tile / tiles_per_batch, r0 = tile - b * tiles_per_batch;
       const int prob = r0 / tiles_per_prob, r = r0 - prob * tiles_per_prob;
@@ -588,15 +712,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       tc::mbar_wait(tfull_bar(acc), acc_phase);
       tc::tc_fence_after();
       if (dbg && tile == (int)blockIdx.x && warp == 2 && lane == 0) dbg[5] = clock64();
-      tc_epilogue_tile<BN, EPI_WARPS>(p, ep, tmem_base + acc * C::ACC_STRIDE, tm, tn, b, q, (warp - 2) >> 2, lane,
-                           reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256) + (warp - 2) * 32 * EPI_LD,
-                           tile == (int)blockIdx.x ? dbg : nullptr);
+      if (RAW && p.tma_c[prob]) {
+        tc_epilogue_tile_tma<BN>(p, ep, prob ? &tm2C : &tmC, prob ? &tm2Cp : &tmCp, tmem_base + acc * C::ACC_STRIDE, tm, tn, b, q, lane,
+                                 smem + C::STAGES * C::STAGE_BYTES + 1024, base + C::STAGES * C::STAGE_BYTES + 1024,
+                                 cbuf, warp == 2 && lane == 0);
+      } else {
+        tc_epilogue_tile<BN, EPI_WARPS>(p, ep, tmem_base + acc * C::ACC_STRIDE, tm, tn, b, q, (warp - 2) >> 2, lane,
+                             reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256) + (warp - 2) * 32 * EPI_LD,
+                             tile == (int)blockIdx.x ? dbg : nullptr);
+      }
       tc::tc_fence_before();
       __syncwarp();
       if (dbg && tile == (int)blockIdx.x && warp == 2 && lane == 0) dbg[6] = clock64();
       if (lane == 0) tc::mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    if (RAW && warp == 2 && lane == 0) tc::tma_store_wait_all();   // staging tiles and C are settled before the CTA leaves
   }
 
   tc::tc_fence_before();
@@ -632,17 +763,17 @@ static EncodeTiledFn get_encode() {
 }
 
 struct MapKey {
-  const void* ptr; int rows, cols, ld, batch, box_rows; long long stride;
+  const void* ptr; int rows, cols, ld, batch, box_rows, box_cols; long long stride;
   bool operator==(const MapKey& o) const {
     return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && batch == o.batch &&
-           box_rows == o.box_rows && stride == o.stride;
+           box_rows == o.box_rows && box_cols == o.box_cols && stride == o.stride;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = reinterpret_cast<size_t>(k.ptr);
     auto mix = [&](size_t v) { h ^= v + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2); };
-    mix(k.rows); mix(k.cols); mix(k.ld); mix(k.batch); mix(k.box_rows); mix((size_t)k.stride);
+    mix(k.rows); mix(k.cols); mix(k.ld); mix(k.batch); mix(k.box_rows); mix(k.box_cols); mix((size_t)k.stride);
     return h;
   }
 };
@@ -651,9 +782,10 @@ static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
 // tensor map of a batched row-major matrix [batch][rows][cols] (row stride ld, batch stride `stride`
 // floats), box = 32 columns x box_rows rows x 1, 128-byte swizzle, zero fill outside the matrix
+// (box_cols < 32: a dense, unswizzled box -- the trailing partial chunk of a C tile)
 static int get_map(const float* ptr, int rows, int cols, int ld, int batch, long long stride, int box_rows,
-                   CUtensorMap* out) {
-  const MapKey key{ptr, rows, cols, ld, batch, box_rows, stride};
+                   CUtensorMap* out, int box_cols = tc::BK) {
+  const MapKey key{ptr, rows, cols, ld, batch, box_rows, box_cols, stride};
   std::lock_guard<std::mutex> lk(g_map_mu);
   auto it = g_maps.find(key);
   if (it != g_maps.end()) { *out = it->second; return 0; }
@@ -661,11 +793,12 @@ static int get_map(const float* ptr, int rows, int cols, int ld, int batch, long
   if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return 1; }
   const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
   const cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(batch > 1 ? stride : (long long)ld * rows) * 4};
-  const cuuint32_t box[3] = {(cuuint32_t)tc::BK, (cuuint32_t)box_rows, 1};
+  const cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   CUtensorMap m;
   const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == tc::BK ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) for rows=%d cols=%d ld=%d batch=%d", (int)r, rows, cols, ld, batch);
@@ -689,6 +822,8 @@ int tc_tune_pdl(int on) { g_tc_pdl = on; return 0; }
 static int g_tc_raw = 1;   // plain FP32 operands, hi/lo split inside the kernel (0: pre-split pairs in HBM)
 int tc_tune_raw(int on) { g_tc_raw = on ? 1 : 0; return 0; }
 bool tc_raw_enabled() { return g_tc_raw != 0; }
+static int g_tc_tma_store = 1;   // raw kernel: C through TMA stores (0: direct stores from the epilogue warps)
+int tc_tune_tma_store(int on) { g_tc_tma_store = on ? 1 : 0; return 0; }
 static int g_tc_exp = 0;
 int tc_tune_exp(int v) { g_tc_exp = v; return 0; }
 static int g_tc_dual = 1;  // pair independent same-shape products into one launch
@@ -708,7 +843,8 @@ static int launch_tc(const TcGemm& g, const TcGemm* g2, int batch, cudaStream_t 
   using C = tc::Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    UGLAD_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    UGLAD_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    RAW ? C::SMEM_RAW : C::SMEM));
     attr_set = true;
   }
   CUtensorMap m[8];
@@ -726,6 +862,21 @@ static int launch_tc(const TcGemm& g, const TcGemm* g2, int batch, cudaStream_t 
     }
   }
   TcParams p;
+  CUtensorMap mc[2], mcp[2];
+  for (int i = 0; i < 2; ++i) {   // raw kernel: C leaves through TMA stores when its rows are 16-byte aligned
+    const TcGemm& q = *gs[i];
+    auto al16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
+    const bool ok = RAW && g_tc_tma_store && q.C_lo == nullptr && q.ldc % 4 == 0 && q.sC % 4 == 0 && al16(q.C_hi) &&
+                    (q.E1_hi == nullptr || (q.E1_lo == nullptr && q.lde1 % 4 == 0 && q.sE1 % 4 == 0 && al16(q.E1_hi)));
+    p.tma_c[i] = ok ? 1 : 0;
+    if (ok) {
+      if (get_map(q.C_hi, q.M, q.N, q.ldc, batch, q.sC, tc::BM, &mc[i])) return 1;
+      mcp[i] = mc[i];
+      if (BN % 32 && get_map(q.C_hi, q.M, q.N, q.ldc, batch, q.sC, tc::BM, &mcp[i], BN % 32)) return 1;
+    } else {
+      mc[i] = mcp[i] = m[0];   // never dereferenced
+    }
+  }
   p.dbg = g_tc_dbg;
   p.M = g.M; p.N = g.N; p.K = g.K; p.batch = batch;
   p.tiles_m = (g.M + tc::BM - 1) / tc::BM;
@@ -745,14 +896,15 @@ static int launch_tc(const TcGemm& g, const TcGemm* g2, int batch, cudaStream_t 
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(RAW ? tc::THREADS_RAW : tc::THREADS);
-  cfg.dynamicSmemBytes = C::SMEM;
+  cfg.dynamicSmemBytes = RAW ? C::SMEM_RAW : C::SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = g_tc_pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  UGLAD_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, RAW>, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], p));
+  UGLAD_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, RAW>, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], mc[0], mc[1],
+                                mcp[0], mcp[1], p));
   profile_end(st);
   UGLAD_CHECK_LAUNCH("tc_gemm_kernel");
   return 0;

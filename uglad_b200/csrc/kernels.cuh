@@ -88,6 +88,7 @@ int launch_tc_gemm2(const TcGemm& g1, const TcGemm& g2, int batch, cudaStream_t 
 int tc_tune_dual(int on);
 int tc_tune_bn(int bn);
 int tc_tune_pdl(int on);
+int tc_tune_tma_store(int on);   // 1 (default): the raw-operand kernel writes C with TMA stores
 int tc_tune_exp(int v);   // developer experiments (see TcParams::exp)
 int tc_tune_raw(int on);   // 1 (default): plain FP32 operands split in shared memory; 0: pre-split hi/lo pairs
 bool tc_raw_enabled();

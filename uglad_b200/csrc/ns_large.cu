@@ -181,6 +181,7 @@ int ns_tune(const char* key, int value) {
   if (!strcmp(key, "tc_pdl")) return tc_tune_pdl(value);
   if (!strcmp(key, "tc_dual")) return tc_tune_dual(value);
   if (!strcmp(key, "tc_raw")) return tc_tune_raw(value);
+  if (!strcmp(key, "tc_tma_store")) return tc_tune_tma_store(value);
   if (!strcmp(key, "tc_exp")) return tc_tune_exp(value);
   return 1;
 }
