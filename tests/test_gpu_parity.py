@@ -192,6 +192,28 @@ def test_eigensolver_path_with_simt_products(dev):
         ops.reset_warm_start()
 
 
+@pytest.mark.parametrize("name", ["d100_lowrho.npz", "d12_raw.npz", "d20_b3_multitask.npz"])
+def test_eigensolver_path_with_presplit_products(dev, name):
+    """The eigenvector products on pre-split (hi, lo) pairs behind "eig_raw" = 0 (the default forms
+    hi/lo inside the tcgen05 kernel from plain operands; D = 12, 20, 100 cover rows that are and are
+    not 16-byte multiples)."""
+    from uglad_b200 import main as ug, ops
+    g = np.load(os.path.join(ROOT, "tests", "golden", name))
+    S = torch.tensor(g["S"], device=dev)
+    ops.tune("eig_raw", 0)
+    try:
+        ops.reset_warm_start()
+        model = load_model(g, "p0")
+        theta, loss = ug.forward_uGLAD(S, model, L=int(g["L"]), INIT_DIAG=int(g["init_diag"]))
+        loss.backward()
+        assert rel(theta.detach().cpu().numpy(), g["theta0"]) < THETA_TOL
+        for k, p in model.named_parameters():
+            assert rel(p.grad.cpu().numpy(), g["g0/" + k]) < 1e-3, k
+    finally:
+        ops.tune("eig_raw", 1)
+        ops.reset_warm_start()
+
+
 def test_warm_start_does_not_change_the_result(dev):
     from uglad_b200 import main as ug, ops
     g = np.load(CASES[0])

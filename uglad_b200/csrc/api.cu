@@ -136,25 +136,31 @@ static int spectral_recon(const float* Vt, const float* f, float* C, int B, int 
 }
 // tcgen05 3xTF32 product of two split [B][D][ldp] matrices: C = A B^T (split or plain output)
 static int tc_mm(const float* Ah, const float* Al, const float* Bh, const float* Bl, float* Ch, float* Cl,
-                 int B, int D, int ldp, cudaStream_t st) {
+                 int B, int D, int ldp, cudaStream_t st, bool padded_out = false) {
   TcGemm g;
   g.A_hi = Ah; g.A_lo = Al; g.B_hi = Bh; g.B_lo = Bl;
   g.M = g.N = g.K = D;
   g.lda = g.ldb = ldp;
   g.sA = g.sB = (long long)D * ldp;
   g.C_hi = Ch; g.C_lo = Cl;
-  g.ldc = Cl ? ldp : D;
-  g.sC = Cl ? (long long)D * ldp : (long long)D * D;
+  g.ldc = (Cl || padded_out) ? ldp : D;
+  g.sC = (Cl || padded_out) ? (long long)D * ldp : (long long)D * D;
   return launch_tc_gemm(g, B, st);
 }
+// eigenvector products on plain FP32 operands (hi/lo formed inside the tcgen05 kernel) instead of
+// pre-split pairs: uglad_tune("eig_raw", 1)
+static int g_eig_raw = 1;
+static bool eig_raw() { return g_eig_raw && tc_raw_enabled(); }
 // C = alpha V diag(f) V^T + beta E1 on the tensor pipe: split / transpose the eigenvectors into
 // `sp` (6 * n2p floats: Vt, V, V diag f as hi/lo pairs), then one tcgen05 product
 static int spectral_recon_tc(const float* Vt, const float* f, float* C, int B, int D, int ldp, size_t n2p,
                              float* sp, float alpha, const float* E1, long long sE1, float beta, cudaStream_t st) {
   float *T = sp, *V = sp + 2 * n2p, *VF = sp + 4 * n2p;
-  if (launch_eigvec_split(Vt, f, B, D, ldp, T, T + n2p, V, V + n2p, VF, VF + n2p, st)) return 1;
+  const bool raw = eig_raw();
+  if (raw ? launch_eigvec_split(Vt, f, B, D, ldp, nullptr, nullptr, V, nullptr, VF, nullptr, st)
+          : launch_eigvec_split(Vt, f, B, D, ldp, T, T + n2p, V, V + n2p, VF, VF + n2p, st)) return 1;
   TcGemm g;
-  g.A_hi = VF; g.A_lo = VF + n2p; g.B_hi = V; g.B_lo = V + n2p;
+  g.A_hi = VF; g.A_lo = raw ? nullptr : VF + n2p; g.B_hi = V; g.B_lo = raw ? nullptr : V + n2p;
   g.M = g.N = g.K = D;
   g.lda = g.ldb = ldp;
   g.sA = g.sB = (long long)D * ldp;
@@ -403,8 +409,13 @@ int uglad_glad_layer_forward(const uglad_dims* d, int k, const float* S, const f
     float* VtSk = ws + w.VtS + (size_t)k * 2 * w.n2p;
     float* VSk = ws + w.VS + (size_t)k * 2 * w.n2p;
     float* VF = ws + w.sp;
-    if (launch_eigvec_split(Vk, fk, B, D, w.ldp, VtSk, VtSk + w.n2p, VSk, VSk + w.n2p, VF, VF + w.n2p, st)) return 1;
-    if (tc_mm(VF, VF + w.n2p, VSk, VSk + w.n2p, Xk, nullptr, B, D, w.ldp, st)) return 1;
+    if (eig_raw()) {   // plain V (kept for the backward) and V diag f; Vt is read in place when its rows are 16-byte multiples
+      if (launch_eigvec_split(Vk, fk, B, D, w.ldp, w.ldp == D ? nullptr : VtSk, nullptr, VSk, nullptr, VF, nullptr, st)) return 1;
+      if (tc_mm(VF, nullptr, VSk, nullptr, Xk, nullptr, B, D, w.ldp, st)) return 1;
+    } else {
+      if (launch_eigvec_split(Vk, fk, B, D, w.ldp, VtSk, VtSk + w.n2p, VSk, VSk + w.n2p, VF, VF + w.n2p, st)) return 1;
+      if (tc_mm(VF, VF + w.n2p, VSk, VSk + w.n2p, Xk, nullptr, B, D, w.ldp, st)) return 1;
+    }
   } else if (spectral_recon(Vk, fk, Xk, B, D, 1.f, nullptr, 0, st)) {
     return 1;
   }
@@ -450,6 +461,22 @@ int uglad_glad_backward(const uglad_dims* d, const float* S, const float* params
       float* U1 = ws + w.sp + 4 * w.n2p;
       float* Gt = ws + w.sp + 6 * w.n2p;
       float* Pm = ws + w.sp + 8 * w.n2p;
+      if (eig_raw()) {   // the same round trip on plain padded matrices
+        const float* VtOp = (w.ldp == D) ? Vk : VtSk;
+        if (launch_z_update_bwd(G, Xk, S, theta_prev, params, d->H, B, D, GXs, GF3,
+                                ws + w.rho_part + (size_t)k * w.nblk * w.NPR, st, nullptr, w.ldp)) return 1;
+        if (tc_mm(VtOp, nullptr, GXs, nullptr, U1, nullptr, B, D, w.ldp, st, true)) return 1;
+        if (tc_mm(U1, nullptr, VtOp, nullptr, Gt, nullptr, B, D, w.ldp, st, true)) return 1;
+        if (launch_phi_split(Gt, nullptr, ws + w.beta + (size_t)k * w.n1, ws + w.sroot + (size_t)k * w.n1,
+                             ws + w.snorm + (size_t)k * B, d->exact_sqrt, B, D, w.ldp,
+                             ws + w.trh_part + (size_t)k * w.nblk, st)) return 1;
+        if (tc_mm(VSk, nullptr, Gt, nullptr, Pm, nullptr, B, D, w.ldp, st, true)) return 1;
+        if (tc_mm(Pm, nullptr, VSk, nullptr, T1, nullptr, B, D, w.ldp, st)) return 1;
+        float* Gn = Gbuf[k & 1];
+        if (launch_gb_finish(T1, GF3, S, B, D, Gn, ws + w.sgb_part + (size_t)k * w.nblk, st)) return 1;
+        G = Gn;
+        continue;
+      }
       if (launch_z_update_bwd(G, Xk, S, theta_prev, params, d->H, B, D, GXs, GF3,
                               ws + w.rho_part + (size_t)k * w.nblk * w.NPR, st, GXs + w.n2p, w.ldp)) return 1;
       if (tc_mm(VtSk, VtSk + w.n2p, GXs, GXs + w.n2p, U1, U1 + w.n2p, B, D, w.ldp, st)) return 1;
@@ -492,8 +519,12 @@ int uglad_glad_backward(const uglad_dims* d, const float* S, const float* params
   } else {
     if (!w.large && ns_use_tc()) {  // theta_0 is symmetric: theta_0 theta_0^T on the tensor pipe
       float* Ts = ws + w.sp;
-      if (launch_tcs_split(ws + w.theta, (long long)D * D, B, D, D, D, w.ldp, Ts, Ts + w.n2p, st)) return 1;
-      if (tc_mm(Ts, Ts + w.n2p, Ts, Ts + w.n2p, T1, nullptr, B, D, w.ldp, st)) return 1;
+      if (eig_raw() && w.ldp == D) {   // theta_0 in place
+        if (tc_mm(ws + w.theta, nullptr, ws + w.theta, nullptr, T1, nullptr, B, D, w.ldp, st)) return 1;
+      } else {
+        if (launch_tcs_split(ws + w.theta, (long long)D * D, B, D, D, D, w.ldp, Ts, Ts + w.n2p, st)) return 1;
+        if (tc_mm(Ts, Ts + w.n2p, Ts, Ts + w.n2p, T1, nullptr, B, D, w.ldp, st)) return 1;
+      }
     } else if (w.large && ns_use_tc() && tc_raw_enabled() && D % 4 == 0) {  // plain operands, split in the kernel
       TcGemm g;
       g.A_hi = ws + w.theta; g.B_hi = ws + w.theta;
@@ -605,6 +636,7 @@ int uglad_profile(int enable, double* total_ms, unsigned long long* launches) {
 
 int uglad_tune(const char* key, int value) {
   if (!key) return 1;
+  if (!strcmp(key, "eig_raw")) { g_eig_raw = value ? 1 : 0; return 0; }
   if (!strcmp(key, "small_d_max")) {
     if (value < 0 || value > UGLAD_SMALL_D_MAX) { set_error("small_d_max must lie in [0, %d]", UGLAD_SMALL_D_MAX); return 1; }
     g_small_d_max = value;

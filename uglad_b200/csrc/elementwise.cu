@@ -180,13 +180,17 @@ __global__ void __launch_bounds__(EW_THREADS) z_update_bwd_kernel(
       gx = gz + fx;
       gt = ft;
     }
-    if (GXlo) {  // split (hi, lo) copy in the padded layout the tcgen05 products read
+    if (ldp) {  // padded [B][D][ldp] layout the tcgen05 products read: a (hi, lo) pair, or plain (GXlo == nullptr)
       const int r = i / D, c = i - r * D;
       const size_t o = (size_t)blockIdx.y * D * ldp + (size_t)r * ldp + c;
-      uint32_t hb;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(gx));
-      GX[o] = __uint_as_float(hb);
-      GXlo[o] = gx - __uint_as_float(hb);
+      if (GXlo) {
+        uint32_t hb;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(gx));
+        GX[o] = __uint_as_float(hb);
+        GXlo[o] = gx - __uint_as_float(hb);
+      } else {
+        GX[o] = gx;
+      }
     } else {
       GX[base + i] = gx;
     }
@@ -273,7 +277,7 @@ __global__ void __launch_bounds__(EW_THREADS) phi_split_kernel(
   for (int idx = blockIdx.x * EW_THREADS + threadIdx.x; idx < n; idx += gridDim.x * EW_THREADS) {
     const int i = idx / D, j = idx - i * D;
     const size_t o = (size_t)b * D * ldp + (size_t)i * ldp + j;
-    const float gt = Gh[o] + Gl[o];
+    const float gt = Gl ? Gh[o] + Gl[o] : Gh[o];
     float C;
     if (exact_sqrt)
       C = 1.f / (sr[i] + sr[j]);
@@ -282,10 +286,14 @@ __global__ void __launch_bounds__(EW_THREADS) phi_split_kernel(
     const float Hh = 0.5f * C * gt;
     if (i == j) tr += Hh;
     const float w = (be[i] + be[j]) * Hh - 0.5f * gt;
-    uint32_t hb;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(w));
-    Gh[o] = __uint_as_float(hb);
-    Gl[o] = w - __uint_as_float(hb);
+    if (Gl) {
+      uint32_t hb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(w));
+      Gh[o] = __uint_as_float(hb);
+      Gl[o] = w - __uint_as_float(hb);
+    } else {
+      Gh[o] = w;
+    }
   }
   const float tot = block_sum(tr, red);
   if (threadIdx.x == 0) trh_part[blockIdx.y * gridDim.x + blockIdx.x] = tot;
@@ -312,10 +320,14 @@ __global__ void eigvec_split_kernel(const float* __restrict__ Vt, const float* _
     float v = 0.f;
     if (k < D && i < D) {
       v = Vt[base + (size_t)k * D + i];
-      uint32_t hb;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
-      Th[pbase + (size_t)k * ldp + i] = __uint_as_float(hb);
-      Tl[pbase + (size_t)k * ldp + i] = v - __uint_as_float(hb);
+      if (Tl) {
+        uint32_t hb;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+        Th[pbase + (size_t)k * ldp + i] = __uint_as_float(hb);
+        Tl[pbase + (size_t)k * ldp + i] = v - __uint_as_float(hb);
+      } else if (Th) {   // plain padded copy (raw operands; skipped when Vt itself has 16-byte rows)
+        Th[pbase + (size_t)k * ldp + i] = v;
+      }
     }
     t[r][threadIdx.x] = v;
   }
@@ -325,14 +337,22 @@ __global__ void eigvec_split_kernel(const float* __restrict__ Vt, const float* _
     if (i < D && k < D) {
       const float v = t[threadIdx.x][r];
       uint32_t hb;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
-      Vh[pbase + (size_t)i * ldp + k] = __uint_as_float(hb);
-      Vl[pbase + (size_t)i * ldp + k] = v - __uint_as_float(hb);
+      if (Vl) {
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+        Vh[pbase + (size_t)i * ldp + k] = __uint_as_float(hb);
+        Vl[pbase + (size_t)i * ldp + k] = v - __uint_as_float(hb);
+      } else {
+        Vh[pbase + (size_t)i * ldp + k] = v;
+      }
       if (Fh) {
         const float w = v * f[(size_t)blockIdx.z * D + k];
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(w));
-        Fh[pbase + (size_t)i * ldp + k] = __uint_as_float(hb);
-        Fl[pbase + (size_t)i * ldp + k] = w - __uint_as_float(hb);
+        if (Fl) {
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(w));
+          Fh[pbase + (size_t)i * ldp + k] = __uint_as_float(hb);
+          Fl[pbase + (size_t)i * ldp + k] = w - __uint_as_float(hb);
+        } else {
+          Fh[pbase + (size_t)i * ldp + k] = w;
+        }
       }
     }
   }
