@@ -22,4 +22,6 @@ for step in range(6):
     off = lib.uglad_workspace_offset(C.byref(dims), b"info")
     info = ws[off:off + 15 * B * 4].view(15, B, 4).cpu().numpy()
     print(f"step {step}: sweeps/layer {info[:, :, 0].mean(1).round(2).tolist()}")
+    sw = info[:, :, 0].astype(int)
+    print(f"   sweep histogram over (layer, graph): {np.bincount(sw.ravel()).tolist()}; max per layer {sw.max(1).tolist()}")
     print(f"   cycles: setup {info[:,:,1].mean():.0f}  sweeps {info[:,:,2].mean():.0f}  tail {info[:,:,3].mean():.0f}; per sweep {info[:,:,2].sum()/info[:,:,0].sum():.0f}", flush=True)

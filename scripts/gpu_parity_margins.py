@@ -8,6 +8,8 @@ from oracle import uglad_oracle as O
 from uglad_b200 import main as ug, ops
 from uglad_b200.glad.glad_params import GladParams
 dev = torch.device("cuda:0")
+for kv in sys.argv[1:]:   # extra knobs, e.g. eig_tol_1e7=40
+    k, v = kv.split("="); ops.tune(k, int(v)); print("knob", k, v)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def rel(a, b):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
@@ -17,7 +19,7 @@ def load_model(g, tag):
     m.load_state_dict({k: torch.tensor(g[f"{tag}/{k}"]) for k in O.PARAM_KEYS})
     return m
 cases = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz"))) + sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "large", "*.npz")))
-for knobs in ({"eig_raw": 1, "tc_raw": 1}, {"eig_raw": 0, "tc_raw": 0}, {"use_tc": 0}):
+for knobs in ({"eig_raw": 1, "tc_raw": 1}, {"eig_raw": 0, "tc_raw": 0}, {"use_tc": 0})[:(1 if len(sys.argv) > 1 else 3)]:
     for k, v in knobs.items(): ops.tune(k, v)
     for path in cases:
         g = np.load(path)

@@ -719,6 +719,7 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
 }
 
 static int g_tune_lp = 0;      // 0 = auto; otherwise force lanes per column pair (4/8/16/32)
+static int g_tune_tol_1e7 = 0;  // 0 = EigArgs::tol; otherwise the cosine tolerance in units of 1e-7
 static int g_tune_keepg = -1;  // -1 = auto (keep G when two buffers fit); 0 / 1 force
 static int g_tune_timing = 0;
 static int g_tune_mma = 1;     // 1 = warm-start product and Rayleigh quotients on the mma.sync tensor path
@@ -726,6 +727,7 @@ static int g_tune_pad = 1;     // 1 = pad shared-memory columns to LP*CH*4 float
 int eig_small_tune(const char* key, int value) {
   if (!strcmp(key, "eig_lp")) { g_tune_lp = value; return 0; }
   if (!strcmp(key, "eig_keepg")) { g_tune_keepg = value; return 0; }
+  if (!strcmp(key, "eig_tol_1e7")) { g_tune_tol_1e7 = value; return 0; }
   if (!strcmp(key, "eig_pad")) { g_tune_pad = value; return 0; }
   if (!strcmp(key, "eig_timing")) { g_tune_timing = value; return 0; }
   if (!strcmp(key, "eig_mma")) { g_tune_mma = value; return 0; }
@@ -781,6 +783,7 @@ int launch_eig_small(const EigArgs& a_in, int B, cudaStream_t st) {
   const size_t extra = 2 * a.ld * sizeof(float) + 32 * sizeof(double) + 32 * sizeof(float) + 16;
   const bool fits2 = 2 * mat + extra <= 227 * 1024;
   a.keepG = (g_tune_keepg < 0) ? (fits2 ? 1 : 0) : (g_tune_keepg && fits2 ? 1 : 0);
+  if (g_tune_tol_1e7 > 0) a.tol = 1e-7f * (float)g_tune_tol_1e7;
   if (!a.keepG) a.warmVt = nullptr;
   const size_t smem = (a.keepG ? 2 : 1) * mat + extra;
 #define UGLAD_EIG_CASE(LP_, CH_)                                                    \
