@@ -316,6 +316,10 @@ def main():
     dev = torch.device("cuda", local_rank)
     group = None
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed to stdout
+        # when NCCL_DEBUG=VERSION/INFO is set in the environment) goes to a file instead
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and "NCCL_DEBUG_FILE" not in os.environ:
+            os.environ["NCCL_DEBUG_FILE"] = os.path.join("/tmp", "uglad_bench_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
 
