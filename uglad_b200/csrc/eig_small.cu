@@ -201,6 +201,9 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
   float* red = reinterpret_cast<float*>(redd + 32);     // [32]
   __shared__ unsigned s_flag;
   __shared__ float s_sigma;
+  constexpr int MAXFIX = 32;              // column pairs the post-sweep check may hand to the fix-up pass
+  __shared__ unsigned s_nfix;
+  __shared__ unsigned s_fix[MAXFIX];
 
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -240,7 +243,7 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
       }
       Gk[idx] = v;
     }
-    if (tid == 0) s_flag = 0u;
+    if (tid == 0) { s_flag = 0u; s_nfix = 0u; }
     trace = block_sum(trace_part, red);
     if (a.shift_mode == 1) {
       float bound;
@@ -488,7 +491,12 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
       if (fmaxoff <= 0.f) break;
       // Barrier-free check of all D(D-1)/2 cosines (no writes): when the sweep above already
       // converged the columns this replaces a whole no-rotation sweep of m synchronised rounds.
-      {
+      // The few pairs that are still above the tolerance after a sweep (typically a handful of
+      // 4950; they sent a fifth of the warm solves into a full extra sweep, and every launch lasts
+      // as long as its slowest graph) are listed and rotated one at a time in a fix-up pass, then
+      // the check runs again; a long list, or a second failed re-check, falls back to a full sweep.
+      bool converged = false;
+      for (int fixrounds = 0;; ++fixrounds) {
         float cmax = 0.f;
         const unsigned gmask = (LP >= 32) ? 0xffffffffu : (((1u << LP) - 1u) << (lane & ~(LP - 1)));
         for (int pp = grp; pp < (D + 1) / 2; pp += ngroups) {
@@ -516,17 +524,33 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
               }
               const float ga = group_sum_masked<LP>(g0 + g1, gmask);
               const float den = al * nrm2[q];
-              if (ga * ga > tol2 * den) cmax = 1.f;
+              if (ga * ga > tol2 * den) {
+                cmax = 1.f;
+                if (gl == 0) {
+                  const unsigned slot = atomicAdd(&s_nfix, 1u);
+                  if (slot < (unsigned)MAXFIX) s_fix[slot] = ((unsigned)p << 16) | (unsigned)q;
+                }
+              }
             }
           }
         }
         if (cmax > 0.f) atomicMax(&s_flag, __float_as_uint(cmax));
         __syncthreads();
         const bool more = __uint_as_float(s_flag) > 0.f;
+        const unsigned nfix = s_nfix;
         __syncthreads();
-        if (tid == 0) s_flag = 0u;
-        if (!more) break;
+        if (tid == 0) { s_flag = 0u; s_nfix = 0u; }
+        if (!more) { converged = true; break; }
+        if (nfix > (unsigned)MAXFIX || fixrounds >= 2) { __syncthreads(); break; }   // full sweep
+        // fix-up: one listed pair per round (they may share columns); every group executes the
+        // same rotation arithmetic, group 0 alone writes
+        for (unsigned f = 0; f < nfix; ++f) {
+          const unsigned pq = s_fix[f];
+          do_pair((int)(pq >> 16), (int)(pq & 0xffffu), grp == 0);
+          __syncthreads();
+        }
       }
+      if (converged) break;
     }
 
     t_sweeps1 = clock64();
