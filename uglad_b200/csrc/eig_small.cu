@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
               const float ga = group_sum_masked<LP>(g0 + g1, gmask);
               const float den = al * nrm2[q];
               if (ga * ga > tol2 * den) {
-                cmax = 1.f;
+                cmax = fmaxf(cmax, ga * ga / den);   // largest squared cosine above the tolerance
                 if (gl == 0) {
                   const unsigned slot = atomicAdd(&s_nfix, 1u);
                   if (slot < (unsigned)MAXFIX) s_fix[slot] = ((unsigned)p << 16) | (unsigned)q;
@@ -536,7 +536,8 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
         }
         if (cmax > 0.f) atomicMax(&s_flag, __float_as_uint(cmax));
         __syncthreads();
-        const bool more = __uint_as_float(s_flag) > 0.f;
+        const float worst2 = __uint_as_float(s_flag);
+        const bool more = worst2 > 0.f;
         const unsigned nfix = s_nfix;
         __syncthreads();
         if (tid == 0) { s_flag = 0u; s_nfix = 0u; }
@@ -549,6 +550,10 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
           do_pair((int)(pq >> 16), (int)(pq & 0xffffu), grp == 0);
           __syncthreads();
         }
+        // A rotation by theta in the (p, q) plane moves cos(p, r) by ~theta cos(q, r) <= theta tol: with
+        // every listed |cos| < 1e-3 the untouched pairs stay within tol (1 + 1e-3) and the re-check
+        // (one more pass over all D^2/2 dot products) is skipped.
+        if (worst2 < 1e-6f) { converged = true; break; }
       }
       if (converged) break;
     }
