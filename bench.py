@@ -47,6 +47,19 @@ WORKLOADS = {
 }
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The one JSON line of the contract, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def synth(B, D, M, seed):
     """Synthetic Erdos-Renyi Gaussian-graphical-model samples, min-max normalised like
     uGLAD_GL.fit does (process_table NORM='min_max')."""
@@ -155,7 +168,7 @@ def run_reference(args, wl, rank, world):
         "e2e": {"value": rate, "unit": "layer-graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -299,6 +312,12 @@ def main():
     ap.add_argument("--workload", default="multitask_d100", choices=sorted(WORKLOADS))
     ap.add_argument("--no-extra", action="store_true", help="skip the extra per-config measurements")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON result: everything else that libraries print there
+    # (NCCL's "NCCL version ..." banner under torchrun, for one) is sent to stderr
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -316,10 +335,6 @@ def main():
     dev = torch.device("cuda", local_rank)
     group = None
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed to stdout
-        # when NCCL_DEBUG=VERSION/INFO is set in the environment) goes to a file instead
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and "NCCL_DEBUG_FILE" not in os.environ:
-            os.environ["NCCL_DEBUG_FILE"] = os.path.join("/tmp", "uglad_bench_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
 
@@ -366,7 +381,7 @@ def main():
             "cpu_baseline": cpu,
             "extra": extra,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
