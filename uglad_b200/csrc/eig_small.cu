@@ -201,9 +201,10 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
   float* red = reinterpret_cast<float*>(redd + 32);     // [32]
   __shared__ unsigned s_flag;
   __shared__ float s_sigma;
-  constexpr int MAXFIX = 32;              // column pairs the post-sweep check may hand to the fix-up pass
+  constexpr int MAXFIX = 64;              // column pairs the post-sweep check may hand to the fix-up pass
   __shared__ unsigned s_nfix;
   __shared__ unsigned s_fix[MAXFIX];
+  __shared__ unsigned s_fixs[MAXFIX];     // the list in ascending (p, q) order: the atomic slots are not reproducible
 
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -543,10 +544,18 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
         if (tid == 0) { s_flag = 0u; s_nfix = 0u; }
         if (!more) { converged = true; break; }
         if (nfix > (unsigned)MAXFIX || fixrounds >= 2) { __syncthreads(); break; }   // full sweep
-        // fix-up: one listed pair per round (they may share columns); every group executes the
-        // same rotation arithmetic, group 0 alone writes
+        // fix-up: one listed pair per round (they may share columns), in ascending (p, q) order so
+        // that the result does not depend on the order in which the groups found them; every group
+        // executes the same rotation arithmetic, group 0 alone writes
+        if ((unsigned)tid < nfix) {
+          const unsigned mine = s_fix[tid];
+          unsigned rank = 0;
+          for (unsigned j = 0; j < nfix; ++j) rank += (s_fix[j] < mine) ? 1u : 0u;
+          s_fixs[rank] = mine;
+        }
+        __syncthreads();
         for (unsigned f = 0; f < nfix; ++f) {
-          const unsigned pq = s_fix[f];
+          const unsigned pq = s_fixs[f];
           do_pair((int)(pq >> 16), (int)(pq & 0xffffu), grp == 0);
           __syncthreads();
         }

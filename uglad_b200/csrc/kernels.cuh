@@ -29,7 +29,9 @@ struct EigArgs {
   int max_sweeps = 40;
   int use_mma = 1;               // warm-start product / Rayleigh quotients via mma.sync (3xTF32)
   int timing = 0;                // developer knob: info[1..3] <- phase cycle counts
-  float tol = 2e-6f;   // cosine threshold; FP32 dot products of ~100 terms resolve ~6e-7, and 1e-6 made a fifth of the warm solves pay a third sweep (measured: -3.4% step time, theta error vs the reference 1.6e-5 -> 1.8e-5)
+  float tol = 1e-6f;   // cosine threshold.  2e-6 is 4 % faster and keeps theta within 1.8e-5 of the reference, but on the
+                       // trained low-threshold golden it left an entry of 1.2e-5 where the reference has an exact zero
+                       // (edge criterion: 1e-5); 1e-6 leaves 2e-6 there (scripts/gpu_edge_margin.py)
 };
 int launch_eig_small(const EigArgs& a, int B, cudaStream_t st);
 int eig_small_tune(const char* key, int value);
