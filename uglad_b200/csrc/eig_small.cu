@@ -547,8 +547,8 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
         // fix-up: one listed pair per round (they may share columns), in ascending (p, q) order so
         // that the result does not depend on the order in which the groups found them; every group
         // executes the same rotation arithmetic, group 0 alone writes
-        if ((unsigned)tid < nfix) {
-          const unsigned mine = s_fix[tid];
+        for (unsigned e = tid; e < nfix; e += nthreads) {   // small D: fewer threads than list entries
+          const unsigned mine = s_fix[e];
           unsigned rank = 0;
           for (unsigned j = 0; j < nfix; ++j) rank += (s_fix[j] < mine) ? 1u : 0u;
           s_fixs[rank] = mine;
