@@ -75,12 +75,22 @@ int uglad_condition_covariance_warm(float* S, int B, int D, float offset, float*
  * diagonal of S (in place) and to wS.  wS / VtS are reused by every later forward.        */
 int uglad_condition_covariance(float* S, int B, int D, float offset, float* wS, float* VtS,
                                float* info, float* scratch, void* stream);
-/* D > uglad_small_d_max(): the large-D path keeps no eigendecomposition (wS / VtS / info are
- * ignored and may be NULL); the repair decision is a Cholesky test of S - 1e-6 I and, for the
- * graphs that fail it, a bisection on the shift.  Host-synchronous.  scratch must hold
+/* The reference decides on float64 eigenvalues; here the smallest eigenvalue is refined in double
+ * before the test (D <= uglad_small_d_max(): Rayleigh quotient of its FP32 eigenvector).
+ * D > uglad_small_d_max(): the large-D path keeps no eigendecomposition (wS / VtS / info are
+ * ignored and may be NULL); an FP32 Cholesky of S - (1e-6 + band) I certifies the common
+ * well-conditioned case, anything closer to the threshold is decided by a float64 Cholesky test and
+ * a float64 bisection on the shift.  Host-synchronous.  scratch must hold
  * uglad_condition_scratch_floats(B, D) floats (for D <= small max that equals
  * uglad_eigh_scratch_floats).                                                             */
 size_t uglad_condition_scratch_floats(int B, int D);
+/* the same with the samples at hand (X[B][M][D] and the column means uglad_covariance wrote): the
+ * smallest eigenvalue that the repair decision and the shift use is then that of the float64
+ * covariance of the samples themselves -- what the reference computes -- instead of that of the
+ * FP32 matrix S.  X / mean may be NULL (then identical to uglad_condition_covariance_warm).   */
+int uglad_condition_covariance_x(float* S, const float* X, const float* mean, int B, int M, int D, float offset,
+                                 float* wS, float* VtS, float* info, float* scratch, const float* warm_Vt,
+                                 const float* warm_w, void* stream);
 /* largest D served by the one-CTA eigensolver; above it the theta update runs the reference's
  * Newton-Schulz iteration as dense products (tcgen05 3xTF32) and logdet / inverses come from a
  * blocked Cholesky.  uglad_eigh itself is only available up to this size.                  */
@@ -122,6 +132,12 @@ int uglad_glad_backward(const uglad_dims* d, const float* S, const float* params
 size_t uglad_loss_scratch_floats(int B, int D);
 int uglad_glasso_loss(const float* theta, const float* S, int B, int D, int S_batch, float Bdiv,
                       float* loss_out, float* grad_theta, float* scratch, void* stream);
+/* the same plus the optional structure prior of main.py:325-334 (struct_theta[B][D][D], may be NULL):
+ * loss += sum log cosh(theta o mask) / Bdiv, mask = (1 - struct_theta) - I, and grad_theta +=
+ * tanh(theta o mask) o mask / Bdiv.                                                          */
+int uglad_glasso_loss_prior(const float* theta, const float* S, const float* struct_theta, int B, int D,
+                            int S_batch, float Bdiv, float* loss_out, float* grad_theta, float* scratch,
+                            void* stream);
 
 /* instrumentation for bench.py: kernels launched by this library since it was loaded, and
  * CUDA-event timing of the dominant kernel (the Jacobi eigensolver): uglad_profile(enable, ..)
@@ -131,7 +147,8 @@ unsigned long long uglad_launch_count(void);
 int uglad_profile(int enable, double* total_ms, unsigned long long* launches);
 /* read (without clearing) what has accumulated since the last uglad_profile call for one kernel
  * class: kind 0 = Jacobi eigensolver (work = algorithmic HBM bytes), kind 1 = tcgen05 3xTF32 GEMM
- * (work = algorithmic flops 2 M N K batch).                                                  */
+ * (work = algorithmic flops 2 M N K batch), kind 2 = the FP32 SIMT flops the eigensolver launches
+ * counted themselves (2 D per column-pair dot product, 8 D per applied rotation; launches = rotations). */
 int uglad_profile_read(int kind, double* total_ms, unsigned long long* launches, double* work);
 
 /* developer knobs used by the tuning scripts and tests: "eig_lp" (lanes per column pair, 0 = auto),

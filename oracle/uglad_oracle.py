@@ -361,3 +361,118 @@ def spectral_forward_backward(S, P, L=15, init_diag=0, lambda_init=1.0, exact_sq
         g["lambda_f.0.bias"] += d1
     return dict(theta=theta, theta0=theta0, loss=loss, grads=g,
                 lam=np.array([sv[0] for sv in saved]), g_lam=g_lams)
+
+
+# --------------------------------------------------------------------------------------
+# mode drivers (main.py:34-226, :338-789) restated on top of the matmul formulation; pinned by
+# tests/golden/modes.npz (the real reference's uGLAD_GL / uGLAD_multitask fits)
+# --------------------------------------------------------------------------------------
+def clean_table_minmax(X) -> np.ndarray:
+    """prepare_data.py:361-516 with fit()'s arguments (NORM='min_max', no variance / condition
+    pruning): drop all-zero rows, fill NaNs with column means, drop constant columns, min-max
+    normalise, drop duplicated columns (first occurrence kept)."""
+    X = np.asarray(X, dtype=np.float64)
+    X = X[~np.all(X == 0, axis=1)]
+    col_mean = np.nanmean(X, axis=0)
+    X = np.where(np.isnan(X), col_mean, X)
+    keep = [j for j in range(X.shape[1]) if np.unique(X[:, j]).size > 1]
+    X = X[:, keep]
+    X = (X - X.min(0)) / (X.max(0) - X.min(0))
+    seen, cols = set(), []
+    for j in range(X.shape[1]):
+        key = X[:, j].tobytes()
+        if key not in seen:
+            seen.add(key)
+            cols.append(j)
+    return X[:, cols]
+
+
+def kfold_blocks(M: int, K: int):
+    """sklearn KFold(n_splits=K) without shuffling: (train, test) index arrays per fold."""
+    sizes = np.full(K, M // K)
+    sizes[: M % K] += 1
+    out, start = [], 0
+    for sz in sizes:
+        test = np.arange(start, start + sz)
+        out.append((np.concatenate([np.arange(0, start), np.arange(start + sz, M)]), test))
+        start += sz
+    return out
+
+
+def _f32(S):
+    return torch.tensor(np.asarray(S), dtype=torch.float32)
+
+
+def init_params_running(theta_init_offset: float = 1.0, nF: int = 3, H: int = 3, dtype=torch.float32):
+    """init_params without re-seeding: the next GladParams drawn from torch's global generator
+    (the CV mode calls init_uGLAD once per fold, main.py:483)."""
+    l1, lH1, l2 = torch.nn.Linear(nF, H), torch.nn.Linear(H, H), torch.nn.Linear(H, 1)
+    f1, f2 = torch.nn.Linear(2, H), torch.nn.Linear(H, 1)
+    vals = [torch.tensor([theta_init_offset]), l1.weight, l1.bias, lH1.weight, lH1.bias, l2.weight, l2.bias,
+            f1.weight, f1.bias, f2.weight, f2.bias]
+    return {k: v.detach().clone().to(dtype).requires_grad_(True) for k, v in zip(PARAM_KEYS, vals)}
+
+
+def fit_direct(X, seed, epochs, lr, L=15, true_theta=None):
+    """uGLAD_GL.fit(mode='direct') (main.py:338-425): the structure prior is the true theta."""
+    X = clean_table_minmax(X)
+    S = _f32(covariance(X[None]))
+    P = init_params(seed)
+    st = None if true_theta is None else _f32(np.asarray(true_theta)[None])
+    theta, _ = train(S, P, epochs, lr, L, 0, struct_theta=st)
+    return theta[0].numpy()
+
+
+def fit_cv(X, seed, epochs, lr, k_fold, L=15):
+    """uGLAD_GL.fit(mode='cv') (main.py:428-550): per fold keep the (post-step) parameters of the
+    epoch with the best held-out loss; the best fold's model is run on the full covariance."""
+    X = clean_table_minmax(X)
+    S = _f32(covariance(X[None]))
+    torch.manual_seed(seed)
+    best = (np.inf, None)
+    for train_idx, test_idx in kfold_blocks(X.shape[0], k_fold):
+        S_tr, S_te = _f32(covariance(X[train_idx][None])), _f32(covariance(X[test_idx][None]))
+        P = init_params_running()
+        opt = torch.optim.Adam(list(P.values()), lr=lr, betas=(0.9, 0.999), eps=1e-8)
+        fold_best = (np.inf, None)
+        for _ in range(epochs):
+            opt.zero_grad()
+            _, ltr = forward_loss(S_tr, P, L, 0)
+            with torch.no_grad():
+                _, lte = forward_loss(S_te, P, L, 0)
+            ltr.backward()
+            opt.step()
+            if float(lte) < fold_best[0]:
+                fold_best = (float(lte), {k: v.detach().clone() for k, v in P.items()})
+        if fold_best[0] < best[0]:
+            best = fold_best
+    with torch.no_grad():
+        theta, _ = forward_loss(S, best[1], L, 0)
+    return theta[0].numpy()
+
+
+def fit_missing(X, seed, epochs, lr, k_fold, L=15):
+    """uGLAD_GL.fit(mode='missing') (main.py:553-644): K row-subsampled covariances trained jointly
+    against the full-data covariance (the loss is divided by ITS batch size, 1), then the consensus."""
+    X = clean_table_minmax(X)   # NaNs are mean-imputed by process_table already
+    S = _f32(covariance(X[None]))
+    S_K = _f32(covariance([X[tr] for tr, _ in kfold_blocks(X.shape[0], k_fold)]))
+    P = init_params(seed)
+    opt = torch.optim.Adam(list(P.values()), lr=lr, betas=(0.9, 0.999), eps=1e-8)
+    theta = None
+    for _ in range(epochs):
+        opt.zero_grad()
+        theta = glad_unrolled(S_K, P, L=L)
+        loss = torch.sum(-torch.logdet(theta) + torch.einsum("ij,bji->b", S[0], theta)) / S.shape[0]
+        loss.backward()
+        opt.step()
+    return consensus_min(theta.detach())[0].numpy()
+
+
+def fit_multitask(Xs, seed, epochs, lr, L=15):
+    """uGLAD_multitask.fit (main.py:155-226, :719-789)."""
+    Xs = [clean_table_minmax(X) for X in Xs]
+    S = _f32(covariance(Xs))
+    P = init_params(seed)
+    theta, _ = train(S, P, epochs, lr, L, 0)
+    return theta.numpy()

@@ -17,7 +17,7 @@ for step in range(6):
     th, loss = ug.forward_uGLAD(S, model, L=15)
     loss.backward(); opt.step()
     torch.cuda.synchronize()
-    ws = ops._warm[next(iter(ops._warm))]
+    ws = next(reversed(ops._warm.values()))
     dims = ops.make_dims(B, D, 15, 3, 0)
     off = lib.uglad_workspace_offset(C.byref(dims), b"info")
     info = ws[off:off + 15 * B * 4].view(15, B, 4).cpu().numpy()

@@ -123,7 +123,102 @@ def make_large_case(name, ref_main, GladParams, prepare_data, D, M, L, seed, row
     print(f"{name}: D={D} L={L} loss0={out['loss0']:.6f} nnz={int(out['theta0_nnz'])}")
 
 
+def _quiet(fn, *a, **k):
+    """Run a reference driver with its progress prints swallowed."""
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def make_mode_cases(ref_main, prepare_data):
+    """The reference's own mode drivers through its sklearn-style wrappers (main.py:34-226):
+    direct with a structure prior, cv, missing (consensus) and multitask -- small D, few epochs.
+    torch.manual_seed(seed) right before fit() fixes the initial GladParams (init_uGLAD runs inside)."""
+    from uglad.utils import metrics as ref_metrics
+    out = {}
+    # --- direct mode with true_theta: the log-cosh structure prior enters the loss (main.py:325-334, :397-403)
+    np.random.seed(31)
+    Xb, theta = prepare_data.get_data(num_nodes=10, sparsity=[0.2, 0.2], num_samples=300, batch_size=1,
+                                      eig_offset=1, w_min=0.5, w_max=1)
+    torch.manual_seed(31)
+    m = ref_main.uGLAD_GL()
+    cmp_ = _quiet(m.fit, Xb[0].copy(), true_theta=theta[0], epochs=10, lr=0.01, L=15, verbose=False, mode="direct")
+    out.update({"direct/X": Xb[0], "direct/true_theta": theta[0], "direct/precision": m.precision_,
+                "direct/covariance": m.covariance_, "direct/location": m.location_,
+                "direct/metric_keys": np.array(sorted(cmp_)), "direct/metric_vals": np.array([cmp_[k] for k in sorted(cmp_)])})
+    # --- cv mode (main.py:428-550), 3 folds
+    np.random.seed(32)
+    Xb, theta = prepare_data.get_data(num_nodes=9, sparsity=[0.2, 0.2], num_samples=210, batch_size=1,
+                                      eig_offset=1, w_min=0.5, w_max=1)
+    torch.manual_seed(32)
+    m = ref_main.uGLAD_GL()
+    _quiet(m.fit, Xb[0].copy(), epochs=10, lr=0.01, L=15, verbose=False, mode="cv", k_fold=3)
+    out.update({"cv/X": Xb[0], "cv/precision": m.precision_})
+    # --- missing mode (main.py:553-644): 20 % NaN dropout, K = 4 row-subsampled batches, consensus
+    np.random.seed(33)
+    Xb, theta = prepare_data.get_data(num_nodes=12, sparsity=[0.2, 0.2], num_samples=242, batch_size=1,
+                                      eig_offset=1, w_min=0.5, w_max=1)
+    Xm = prepare_data.add_noise_dropout(Xb, dropout=0.2)[0]
+    torch.manual_seed(33)
+    m = ref_main.uGLAD_GL()
+    _quiet(m.fit, Xm.copy(), epochs=10, lr=0.01, L=15, verbose=False, mode="missing", k_fold=4)
+    out.update({"missing/X": Xm, "missing/precision": m.precision_, "missing/covariance": m.covariance_})
+    # --- multitask (main.py:155-226, :719-789): ragged sample counts, one shared model
+    np.random.seed(34)
+    Xs = [prepare_data.get_data(num_nodes=8, sparsity=[0.2, 0.3], num_samples=mm, batch_size=1, eig_offset=1,
+                                w_min=0.5, w_max=1)[0][0] for mm in (120, 150, 120)]
+    torch.manual_seed(34)
+    mt = ref_main.uGLAD_multitask()
+    _quiet(mt.fit, [x.copy() for x in Xs], epochs=10, lr=0.01, L=15, verbose=False)
+    for i, x in enumerate(Xs):
+        out[f"multitask/X{i}"] = x
+    out.update({"multitask/precision": mt.precision_, "multitask/covariance": mt.covariance_})
+    # --- metrics.report_metrics_all (metrics.py:25-108) on random sparse symmetric pairs
+    rng = np.random.default_rng(35)
+    for i in range(4):
+        d = 12 + 3 * i
+        tg = np.triu((rng.random((d, d)) < 0.25) * rng.uniform(0.5, 1.0, (d, d)), 1)
+        pg = np.triu((rng.random((d, d)) < 0.3) * rng.standard_normal((d, d)), 1)
+        pg = np.where(rng.random((d, d)) < 0.5, pg, np.triu(tg * rng.standard_normal((d, d)), 1))
+        tg, pg = tg + tg.T + np.eye(d), pg + pg.T + np.eye(d)
+        r = ref_metrics.report_metrics_all(tg, pg)
+        out[f"metrics/{i}/true"], out[f"metrics/{i}/pred"] = tg, pg
+        out[f"metrics/{i}/keys"] = np.array(sorted(r))
+        out[f"metrics/{i}/vals"] = np.array([r[k] for k in sorted(r)])
+    # --- process_table (prepare_data.py:361-516): zero rows, NaNs, a constant and a duplicated column; and the
+    #     condition-number pruning loop on nearly collinear columns
+    import pandas as pd
+    rng = np.random.default_rng(36)
+    T = rng.random((40, 8))
+    T[3] = 0.0
+    T[17] = 0.0
+    T[5, 2] = np.nan
+    T[9, 6] = np.nan
+    T[:, 4] = 0.7
+    T[:, 7] = T[:, 1]
+    out["table/raw"] = T
+    out["table/minmax"] = np.array(_quiet(prepare_data.process_table, pd.DataFrame(T.copy()), NORM="min_max", VERBOSE=False))
+    out["table/mean"] = np.array(_quiet(prepare_data.process_table, pd.DataFrame(T.copy()), NORM="mean", VERBOSE=False))
+    Z = rng.standard_normal((60, 9))
+    Z[:, 6] = Z[:, 0] + 1e-3 * rng.standard_normal(60)
+    Z[:, 7] = Z[:, 1] - Z[:, 2] + 1e-3 * rng.standard_normal(60)
+    Z[:, 8] = Z[:, 3] + Z[:, 4] + 1e-2 * rng.standard_normal(60)
+    out["table/collinear"] = Z
+    pruned = _quiet(prepare_data.process_table, pd.DataFrame(Z.copy()), NORM="min_max", COND_NUM=200.0, eigval_th=1e-3, VERBOSE=False)
+    out["table/collinear_kept"] = np.array(list(pruned.columns), dtype=np.int64)
+    out["table/collinear_out"] = np.array(pruned)
+    np.savez_compressed(os.path.join(HERE, "modes.npz"), **out)
+    print("modes: direct(struct prior) / cv / missing / multitask precision_, metrics, process_table;",
+          "kept columns under COND_NUM=200:", out["table/collinear_kept"].tolist())
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "modes":
+        torch.set_num_threads(1)
+        ref_main, ref_glad, GladParams, prepare_data = import_reference()
+        make_mode_cases(ref_main, prepare_data)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "large":
         ref_main, ref_glad, GladParams, prepare_data = import_reference()
         make_large_case("d1000_m10000", ref_main, GladParams, prepare_data, D=1000, M=10000, L=15, seed=17,

@@ -78,3 +78,27 @@ def test_two_shards_reproduce_the_single_process_result(tmp_path):
         assert np.allclose(g["grad"], grad, rtol=2e-4, atol=1e-6)
         assert abs(float(g["loss"][0]) - loss.item()) < 1e-5 * max(1.0, abs(loss.item()))
     assert np.allclose(got, theta.detach().numpy(), rtol=1e-5, atol=1e-6)
+
+
+def _consensus_worker(rank, world, port, theta_all, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from uglad_b200 import main as ug
+    shard = np.array_split(np.arange(theta_all.shape[0]), world)[rank]
+    out = ug.get_final_precision_from_batch(theta_all[shard].clone(), type="min", group=dist.group.WORLD)
+    np.save(os.path.join(out_dir, f"cons{rank}.npy"), out.numpy())
+    dist.destroy_process_group()
+
+
+def test_sharded_consensus_is_bit_identical_to_the_single_process_result(tmp_path):
+    """main.py:673-716 over ranks: K = 5 precision matrices split 3 + 2; all-reduce(MIN) of |theta| and
+    all-reduce(SUM) of sign(theta) are exact, so every rank holds the single-process consensus."""
+    rng = np.random.default_rng(4)
+    theta_all = torch.tensor(rng.standard_normal((5, 9, 9)), dtype=torch.float32)
+    theta_all[:, 2, 3] = torch.tensor([0.5, -0.5, 0.0, 0.25, -0.25])     # a sign tie resolves to +
+    theta_all[:, 4, 4] = 0.0
+    mp.spawn(_consensus_worker, args=(2, _free_port(), theta_all, str(tmp_path)), nprocs=2, join=True)
+    want = O.consensus_min(theta_all).numpy()
+    for r in range(2):
+        assert np.array_equal(np.load(tmp_path / f"cons{r}.npy"), want)

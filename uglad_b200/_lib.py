@@ -34,6 +34,7 @@ SIGNATURES = {
     "uglad_eigh_warm": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "uglad_condition_covariance_warm": (_I, [_P, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
     "uglad_condition_scratch_floats": (_Z, [_I, _I]),
+    "uglad_condition_covariance_x": (_I, [_P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
     "uglad_small_d_max": (_I, []),
     "uglad_workspace_floats": (_Z, [_DP]),
     "uglad_workspace_offset": (_Z, [_DP, C.c_char_p]),
@@ -43,6 +44,7 @@ SIGNATURES = {
     "uglad_glad_backward": (_I, [_DP, _P, _P, _P, _P, _P, _P, _P, _P]),
     "uglad_loss_scratch_floats": (_Z, [_I, _I]),
     "uglad_glasso_loss": (_I, [_P, _P, _I, _I, _I, _F, _P, _P, _P, _P]),
+    "uglad_glasso_loss_prior": (_I, [_P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P]),
     "uglad_launch_count": (C.c_ulonglong, []),
     "uglad_profile": (_I, [_I, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),
     "uglad_profile_read": (_I, [_I, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong), C.POINTER(C.c_double)]),

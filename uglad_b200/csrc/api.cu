@@ -41,6 +41,10 @@ void profile_begin(cudaStream_t st, int kind, double work) {
   cudaEventRecord(e.a, st);
   g_prof_events.push_back(e);
 }
+// FP32 work of the Jacobi kernel, counted by the kernel itself while profiling is on
+static unsigned long long* g_eig_counters = nullptr;   // device: {column-pair dot products, applied rotations}
+static double g_eig_flop_scale_D = 0.0;                 // D of the launches counted (one shape per profiling pass)
+unsigned long long* profile_eig_counters() { return g_prof_on ? g_eig_counters : nullptr; }
 void profile_end(cudaStream_t st) {
   if (!g_prof_on) return;
   std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -179,6 +183,7 @@ static int bgemm(const float* A, int tA, const float* Bm, int tB, float* C, int 
 }
 
 int launch_eig(const EigArgs& a, int B, cudaStream_t st) {
+  if (g_prof_on) g_eig_flop_scale_D = (double)a.D;
   if (a.D <= UGLAD_SMALL_D_MAX) return launch_eig_small(a, B, st);
   set_error("eigensolver: D=%d > %d; the large-D path does not use an eigendecomposition (DESIGN.md)", a.D, UGLAD_SMALL_D_MAX);
   return 1;
@@ -259,52 +264,86 @@ int uglad_eigh(const float* A, int B, int D, int shift_mode, float* w, float* Vt
   return uglad_eigh_warm(A, B, D, shift_mode, w, Vt, info, scratch, nullptr, nullptr, stream);
 }
 
-// prepare_data.py:345-355 for D > small_d_max(): "min eig <= 1e-6" is decided by a Cholesky
-// factorisation of S - 1e-6 I; only graphs that fail it need the eigenvalue itself, found by
-// exponential search + bisection on the shift (host-driven: this runs once per fit).
-static int condition_large(float* S, int B, int D, float offset, float* scratch, cudaStream_t st) {
+// prepare_data.py:345-355 for D > small_d_max() (no eigendecomposition is kept on this path).
+// The reference decides "min eig <= 1e-6" on float64 eigenvalues.  Here:
+//   1. FP32 blocked Cholesky of S - (1e-6 + band_b) I, band_b = 32 sqrt(D) eps32 trace(S_b) (a generous
+//      multiple of the factorisation's backward error).  Success certifies min eig > 1e-6: no repair.
+//      This is the only work for a well-conditioned covariance.
+//   2. Graphs that fail it are decided in double (chol_pd_test_f64: exact up to the rounding of S
+//      itself): S - 1e-6 I positive definite -> no repair; otherwise the eigenvalue is bracketed
+//      (S - hi I not PD, S - lo I PD) by an exponential search and bisected to 1e-10 in double.
+// Host-driven (this runs once per fit).
+static int condition_large(float* S, int B, int D, float offset, float* scratch, const float* X, const float* mean,
+                           int M, cudaStream_t st) {
   const size_t n2 = (size_t)B * D * D;
   float* T = scratch;
   float* mu_dev = T + al4(n2);
   float* cs = mu_dev + al4(B);
-  std::vector<float> lo(B), hi(B, 1e-6f), mu(B, 1e-6f), step(B, 1e-6f);
-  std::vector<int> fail(B), found_lo(B, 0), need(B, 0);
-  auto test = [&]() -> int {
-    UGLAD_CUDA(cudaMemcpyAsync(mu_dev, mu.data(), B * sizeof(float), cudaMemcpyHostToDevice, st));
-    if (launch_copy_shift(S, (long long)D * D, B, D, 0.f, nullptr, T, st)) return 1;
-    if (chol_factor(T, B, D, 0.f, mu_dev, nullptr, cs, st)) return 1;
-    UGLAD_CUDA(cudaMemcpyAsync(fail.data(), chol_fail_flags(cs, B, D), B * sizeof(int), cudaMemcpyDeviceToHost, st));
-    UGLAD_CUDA(cudaStreamSynchronize(st));
-    return 0;
-  };
-  if (test()) return 1;
+  double* work64 = reinterpret_cast<double*>(cs + al4(chol_scratch_floats(B, D)));
+  double* mu64_dev = work64 + n2;
+  int* active_dev = reinterpret_cast<int*>(mu64_dev + B);
+  int* fail64_dev = active_dev + B;
+  double* S64 = (X && mean && M > 0) ? reinterpret_cast<double*>(fail64_dev + al4(B)) : nullptr;
+  std::vector<float> tr(B), mu(B);
+  std::vector<int> fail(B);
+  if (launch_trace(S, B, D, mu_dev, st)) return 1;
+  UGLAD_CUDA(cudaMemcpyAsync(tr.data(), mu_dev, B * sizeof(float), cudaMemcpyDeviceToHost, st));
+  UGLAD_CUDA(cudaStreamSynchronize(st));
+  for (int b = 0; b < B; ++b) mu[b] = 1e-6f + 32.f * sqrtf((float)D) * 5.96e-8f * fabsf(tr[b]);
+  UGLAD_CUDA(cudaMemcpyAsync(mu_dev, mu.data(), B * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (launch_copy_shift(S, (long long)D * D, B, D, 0.f, nullptr, T, st)) return 1;
+  if (chol_factor(T, B, D, 0.f, mu_dev, nullptr, cs, st)) return 1;
+  UGLAD_CUDA(cudaMemcpyAsync(fail.data(), chol_fail_flags(cs, B, D), B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  UGLAD_CUDA(cudaStreamSynchronize(st));
+  std::vector<int> need(B, 0);
   bool any = false;
   for (int b = 0; b < B; ++b) { need[b] = fail[b]; any |= fail[b] != 0; }
   if (!any) return 0;
+  // ---- float64 decision for the graphs the FP32 test could not certify
+  std::vector<double> lo(B, 0.0), hi(B, 1e-6), m64(B, 1e-6), step(B, 1e-6);
+  std::vector<int> found_lo(B, 0), active(B, 0);
+  auto test64 = [&]() -> int {
+    UGLAD_CUDA(cudaMemcpyAsync(mu64_dev, m64.data(), B * sizeof(double), cudaMemcpyHostToDevice, st));
+    UGLAD_CUDA(cudaMemcpyAsync(active_dev, active.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (chol_pd_test_f64(S, S64, B, D, mu64_dev, active_dev, work64, fail64_dev, st)) return 1;
+    UGLAD_CUDA(cudaMemcpyAsync(fail.data(), fail64_dev, B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    UGLAD_CUDA(cudaStreamSynchronize(st));
+    return 0;
+  };
+  active = need;
+  if (S64) {   // decide on the float64 covariance of the samples themselves (free of the rounding of S)
+    UGLAD_CUDA(cudaMemcpyAsync(active_dev, active.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (launch_cov_f64(X, mean, B, M, D, active_dev, S64, st)) return 1;
+  }
+  if (test64()) return 1;
+  any = false;
+  for (int b = 0; b < B; ++b) { if (need[b] && !fail[b]) need[b] = 0; any |= need[b] != 0; }
+  if (!any) return 0;
   // invariant: S - hi I is not positive definite (hi >= min eig); search lo with S - lo I positive definite
-  for (int it = 0; it < 64; ++it) {
+  const double width = 1e-10;
+  for (int it = 0; it < 200; ++it) {
     bool pending = false;
     for (int b = 0; b < B; ++b) {
-      if (!need[b]) { mu[b] = 0.f; continue; }   // result ignored
-      if (!found_lo[b]) { mu[b] = hi[b] - step[b]; pending = true; }
-      else if (hi[b] - lo[b] > 2e-8f * fmaxf(1.f, fabsf(lo[b]) * 1e2f)) { mu[b] = 0.5f * (lo[b] + hi[b]); pending = true; }
-      else mu[b] = lo[b];
+      active[b] = 0;
+      if (!need[b]) continue;
+      if (!found_lo[b]) { m64[b] = hi[b] - step[b]; active[b] = 1; pending = true; }
+      else if (hi[b] - lo[b] > width) { m64[b] = 0.5 * (lo[b] + hi[b]); active[b] = 1; pending = true; }
     }
     if (!pending) break;
-    if (test()) return 1;
+    if (test64()) return 1;
     for (int b = 0; b < B; ++b) {
-      if (!need[b]) continue;
+      if (!active[b]) continue;
       if (!found_lo[b]) {
-        if (fail[b]) { hi[b] = mu[b]; step[b] *= 4.f; }
-        else { lo[b] = mu[b]; found_lo[b] = 1; }
-      } else if (hi[b] - lo[b] > 2e-8f * fmaxf(1.f, fabsf(lo[b]) * 1e2f)) {
-        if (fail[b]) hi[b] = mu[b]; else lo[b] = mu[b];
+        if (fail[b]) { hi[b] = m64[b]; step[b] *= 4.0; }
+        else { lo[b] = m64[b]; found_lo[b] = 1; }
+      } else {
+        if (fail[b]) hi[b] = m64[b]; else lo[b] = m64[b];
       }
     }
   }
   std::vector<float> add(B, 0.f);
   for (int b = 0; b < B; ++b)
-    if (need[b]) add[b] = offset - 0.5f * (lo[b] + hi[b]);
+    if (need[b]) add[b] = (float)((double)offset - 0.5 * (lo[b] + hi[b]));
   UGLAD_CUDA(cudaMemcpyAsync(mu_dev, add.data(), B * sizeof(float), cudaMemcpyHostToDevice, st));
   if (launch_add_diag(S, B, D, mu_dev, st)) return 1;
   UGLAD_CUDA(cudaStreamSynchronize(st));  // `add` lives on this stack frame
@@ -313,18 +352,26 @@ static int condition_large(float* S, int B, int D, float offset, float* scratch,
 
 size_t uglad_condition_scratch_floats(int B, int D) {
   if (D <= small_d_max()) return eig_scratch_floats(B, D);
-  return al4((size_t)B * D * D) + al4(B) + al4(chol_scratch_floats(B, D));
+  // T | mu | Cholesky scratch | float64: factor [B][D][D], shifts [B] | int: active [B], fail [B] |
+  // float64 covariance of the samples [B][D][D] (uglad_condition_covariance_x)
+  return al4((size_t)B * D * D) + al4(B) + al4(chol_scratch_floats(B, D)) + 2 * ((size_t)B * D * D + B) + 2 * al4(B) + 8 +
+         2 * (size_t)B * D * D;
 }
 
+int uglad_condition_covariance_x(float* S, const float* X, const float* mean, int B, int M, int D, float offset,
+                                 float* wS, float* VtS, float* info, float* scratch, const float* warm_Vt,
+                                 const float* warm_w, void* stream) {
+  if (D > small_d_max()) {
+    if (!S || !scratch || B <= 0) { set_error("condition_covariance: bad arguments"); return 1; }
+    return condition_large(S, B, D, offset, scratch, X, mean, M, (cudaStream_t)stream);
+  }
+  if (uglad_eigh_warm(S, B, D, 1, wS, VtS, info, scratch, warm_Vt, warm_w, stream)) return 1;
+  return launch_condition(S, wS, VtS, B, D, offset, X, mean, M, (cudaStream_t)stream);
+}
 int uglad_condition_covariance_warm(float* S, int B, int D, float offset, float* wS, float* VtS,
                                     float* info, float* scratch, const float* warm_Vt, const float* warm_w,
                                     void* stream) {
-  if (D > small_d_max()) {
-    if (!S || !scratch || B <= 0) { set_error("condition_covariance: bad arguments"); return 1; }
-    return condition_large(S, B, D, offset, scratch, (cudaStream_t)stream);
-  }
-  if (uglad_eigh_warm(S, B, D, 1, wS, VtS, info, scratch, warm_Vt, warm_w, stream)) return 1;
-  return launch_condition(S, wS, B, D, offset, (cudaStream_t)stream);
+  return uglad_condition_covariance_x(S, nullptr, nullptr, B, 0, D, offset, wS, VtS, info, scratch, warm_Vt, warm_w, stream);
 }
 int uglad_condition_covariance(float* S, int B, int D, float offset, float* wS, float* VtS,
                                float* info, float* scratch, void* stream) {
@@ -553,6 +600,11 @@ size_t uglad_loss_scratch_floats(int B, int D) {
 
 int uglad_glasso_loss(const float* theta, const float* S, int B, int D, int S_batch, float Bdiv,
                       float* loss_out, float* grad_theta, float* scratch, void* stream) {
+  return uglad_glasso_loss_prior(theta, S, nullptr, B, D, S_batch, Bdiv, loss_out, grad_theta, scratch, stream);
+}
+
+int uglad_glasso_loss_prior(const float* theta, const float* S, const float* struct_theta, int B, int D, int S_batch,
+                            float Bdiv, float* loss_out, float* grad_theta, float* scratch, void* stream) {
   if (!theta || !S || !loss_out || !scratch || B <= 0 || D <= 0) { set_error("glasso_loss: bad arguments"); return 1; }
   if (S_batch != 1 && S_batch != B) { set_error("glasso_loss: S_batch=%d must be 1 or B=%d", S_batch, B); return 1; }
   cudaStream_t st = (cudaStream_t)stream;
@@ -571,7 +623,10 @@ int uglad_glasso_loss(const float* theta, const float* S, int B, int D, int S_ba
     if (chol_factor(Lf, B, D, 0.f, nullptr, logdet, cs, st)) return 1;
     if (launch_loss_terms(theta, S, sSl, logdet, B, D, Bdiv, lpart, lossb, loss_out,
                           reinterpret_cast<unsigned*>(counter), st)) return 1;
-    if (grad_theta) return chol_inverse(Lf, B, D, W, grad_theta, -1.0f / Bdiv, S, sSl, 1.0f / Bdiv, cs, st);
+    if (grad_theta && chol_inverse(Lf, B, D, W, grad_theta, -1.0f / Bdiv, S, sSl, 1.0f / Bdiv, cs, st)) return 1;
+    if (struct_theta)
+      return launch_struct_prior(theta, struct_theta, B, D, Bdiv, grad_theta, lpart, loss_out,
+                                 reinterpret_cast<unsigned*>(counter) + 1, st);
     return 0;
   }
   float* Vt = scratch;
@@ -595,9 +650,13 @@ int uglad_glasso_loss(const float* theta, const float* S, int B, int D, int S_ba
     const int ldp = (D + 3) & ~3;
     const size_t n2p = al4((size_t)B * D * ldp);
     float* sp = escr + al4(eig_scratch_floats(B, D));
-    return spectral_recon_tc(Vt, f, grad_theta, B, D, ldp, n2p, sp, 1.0f / Bdiv, S, sS, 1.0f / Bdiv, st);
+    if (spectral_recon_tc(Vt, f, grad_theta, B, D, ldp, n2p, sp, 1.0f / Bdiv, S, sS, 1.0f / Bdiv, st)) return 1;
+  } else if (grad_theta && spectral_recon(Vt, f, grad_theta, B, D, 1.0f / Bdiv, S, sS, st)) {
+    return 1;
   }
-  if (grad_theta) return spectral_recon(Vt, f, grad_theta, B, D, 1.0f / Bdiv, S, sS, st);
+  if (struct_theta)
+    return launch_struct_prior(theta, struct_theta, B, D, Bdiv, grad_theta, lpart, loss_out,
+                               reinterpret_cast<unsigned*>(counter) + 1, st);
   return 0;
 }
 
@@ -605,6 +664,17 @@ unsigned long long uglad_launch_count(void) { return g_launches.load(); }
 
 int uglad_profile_read(int kind, double* total_ms, unsigned long long* launches, double* work) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (kind == 2) {   // FP32 flops the eigensolver launches counted: 2 D per dot product, 8 D per applied rotation
+    unsigned long long c[2] = {0, 0};
+    if (g_eig_counters) {
+      cudaDeviceSynchronize();
+      cudaMemcpy(c, g_eig_counters, sizeof(c), cudaMemcpyDeviceToHost);
+    }
+    if (total_ms) *total_ms = 0.0;
+    if (launches) *launches = c[1];
+    if (work) *work = (2.0 * (double)c[0] + 8.0 * (double)c[1]) * g_eig_flop_scale_D;
+    return 0;
+  }
   double tot = 0.0, wk = 0.0;
   unsigned long long n = 0;
   for (auto& e : g_prof_events) {
@@ -631,6 +701,10 @@ int uglad_profile(int enable, double* total_ms, unsigned long long* launches) {
   }
   g_prof_events.clear();
   g_prof_on = enable != 0;
+  if (g_prof_on) {
+    if (!g_eig_counters && cudaMalloc(&g_eig_counters, 2 * sizeof(unsigned long long)) != cudaSuccess) g_eig_counters = nullptr;
+    if (g_eig_counters) cudaMemset(g_eig_counters, 0, 2 * sizeof(unsigned long long));
+  }
   return 0;
 }
 

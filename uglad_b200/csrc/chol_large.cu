@@ -313,6 +313,113 @@ int chol_inverse(const float* Lf, int B, int D, float* W, float* Ainv, float alp
   return launch_gemm_auto(g, B, st);
 }
 
+// ---- float64 positive-definiteness test (covariance repair decision, prepare_data.py:345-355) ------
+// The reference decides "min eig <= 1e-6" on float64 eigenvalues.  An FP32 factorisation carries a
+// backward error of ~sqrt(D) eps32 ||S|| -- above the threshold itself -- so whenever the FP32 test is
+// not conclusive (api.cu: condition_large) the decision is taken here: left-looking Cholesky of
+// S - shift[b] I in double, one CTA per graph, the factor kept transposed (Lt[k][i] = L[i][k]) so that
+// the threads' reads are coalesced.  D^3/3 double FMAs through one SM: ~10 ms at D = 1000; it only runs
+// for ill-conditioned covariances, once per fit.  fail[b] = 1 when a pivot is not positive.
+__global__ void __launch_bounds__(1024) chol_pd_test_f64_kernel(const float* __restrict__ S, const double* __restrict__ S64, int D,
+                                                                const double* __restrict__ shift,
+                                                                const int* __restrict__ active, double* __restrict__ work,
+                                                                int* __restrict__ fail) {
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  if (active && !active[b]) return;
+  __shared__ double s_piv;
+  const float* Sb = S ? S + (size_t)b * D * D : nullptr;
+  const double* Sd = S64 ? S64 + (size_t)b * D * D : nullptr;
+  double* Lt = work + (size_t)b * D * D;
+  const double sh = shift[b];
+  for (int j = 0; j < D; ++j) {
+    // column j of L for the rows i >= j owned by this thread
+    for (int i = j + tid; i < D; i += nt) {
+      double acc = (Sd ? Sd[(size_t)i * D + j] : (double)Sb[(size_t)i * D + j]) - ((i == j) ? sh : 0.0);
+      const double* lj = Lt + j;   // Lt[k][j], stride D
+      const double* li = Lt + i;
+      int k = 0;
+      for (; k + 4 <= j; k += 4) {
+        const double a0 = li[(size_t)k * D], a1 = li[(size_t)(k + 1) * D], a2 = li[(size_t)(k + 2) * D], a3 = li[(size_t)(k + 3) * D];
+        const double c0 = lj[(size_t)k * D], c1 = lj[(size_t)(k + 1) * D], c2 = lj[(size_t)(k + 2) * D], c3 = lj[(size_t)(k + 3) * D];
+        acc -= a0 * c0 + a1 * c1 + a2 * c2 + a3 * c3;
+      }
+      for (; k < j; ++k) acc -= li[(size_t)k * D] * lj[(size_t)k * D];
+      if (i == j) s_piv = acc;
+      Lt[(size_t)j * D + i] = acc;   // unscaled for now
+    }
+    __syncthreads();
+    const double piv = s_piv;
+    if (!(piv > 0.0)) {
+      if (tid == 0) fail[b] = 1;
+      return;   // uniform
+    }
+    const double ir = 1.0 / sqrt(piv);
+    for (int i = j + tid; i < D; i += nt) Lt[(size_t)j * D + i] *= ir;
+    __syncthreads();
+  }
+  if (tid == 0) fail[b] = 0;
+}
+int chol_pd_test_f64(const float* S, const double* S64, int B, int D, const double* shift_dev, const int* active_dev,
+                     double* work, int* fail_dev, cudaStream_t st) {
+  int threads = ((D + 31) / 32) * 32;
+  if (threads > 1024) threads = 1024;
+  if (threads < 64) threads = 64;
+  chol_pd_test_f64_kernel<<<B, threads, 0, st>>>(S, S64, D, shift_dev, active_dev, work, fail_dev);
+  UGLAD_CHECK_LAUNCH("chol_pd_test_f64_kernel");
+  return 0;
+}
+// float64 covariance of the samples for the graphs marked active (the matrix the reference decides on):
+// S64[b] = (X_b - mean_b)^T (X_b - mean_b) / M.  16 x 16 output tile per block, 16 samples per step.
+__global__ void __launch_bounds__(256) cov_f64_kernel(const float* __restrict__ X, const float* __restrict__ mean, int M, int D,
+                                                      const int* __restrict__ active, double* __restrict__ S64) {
+  const int b = blockIdx.z;
+  if (active && !active[b]) return;
+  if (blockIdx.x > blockIdx.y) return;   // lower tiles; mirrored below
+  __shared__ double ta[16][17], tb[16][17];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int i0 = blockIdx.y * 16, j0 = blockIdx.x * 16;
+  const float* Xb = X + (size_t)b * M * D;
+  const float* mb = mean + (size_t)b * D;
+  const double mi = (i0 + tx < D) ? (double)mb[i0 + tx] : 0.0, mj = (j0 + tx < D) ? (double)mb[j0 + tx] : 0.0;
+  double acc = 0.0;
+  for (int m0 = 0; m0 < M; m0 += 16) {
+    const int m = m0 + ty;
+    ta[ty][tx] = (m < M && i0 + tx < D) ? (double)Xb[(size_t)m * D + i0 + tx] - mi : 0.0;
+    tb[ty][tx] = (m < M && j0 + tx < D) ? (double)Xb[(size_t)m * D + j0 + tx] - mj : 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc += ta[k][ty] * tb[k][tx];
+    __syncthreads();
+  }
+  const int i = i0 + ty, j = j0 + tx;
+  if (i < D && j < D) {
+    const double v = acc / (double)M;
+    S64[(size_t)b * D * D + (size_t)i * D + j] = v;
+    S64[(size_t)b * D * D + (size_t)j * D + i] = v;
+  }
+}
+int launch_cov_f64(const float* X, const float* mean, int B, int M, int D, const int* active_dev, double* S64,
+                   cudaStream_t st) {
+  dim3 grid((D + 15) / 16, (D + 15) / 16, B);
+  cov_f64_kernel<<<grid, 256, 0, st>>>(X, mean, M, D, active_dev, S64);
+  UGLAD_CHECK_LAUNCH("cov_f64_kernel");
+  return 0;
+}
+// trace of every graph (the scale of the FP32 factorisation's backward error)
+__global__ void trace_kernel(const float* __restrict__ S, int D, float* __restrict__ out) {
+  __shared__ float red[32];
+  const float* Sb = S + (size_t)blockIdx.x * D * D;
+  float t = 0.f;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) t += Sb[(size_t)i * D + i];
+  t = block_sum(t, red);
+  if (threadIdx.x == 0) out[blockIdx.x] = t;
+}
+int launch_trace(const float* S, int B, int D, float* out, cudaStream_t st) {
+  trace_kernel<<<B, 256, 0, st>>>(S, D, out);
+  UGLAD_CHECK_LAUNCH("trace_kernel");
+  return 0;
+}
+
 int launch_copy_shift(const float* src, long long sSrc, int B, int D, float shift, const float* shift_dev,
                       float* dst, cudaStream_t st) {
   dim3 grid(64, B);

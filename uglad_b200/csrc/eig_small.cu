@@ -205,6 +205,8 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
   __shared__ unsigned s_nfix;
   __shared__ unsigned s_fix[MAXFIX];
   __shared__ unsigned s_fixs[MAXFIX];     // the list in ascending (p, q) order: the atomic slots are not reproducible
+  __shared__ int s_stat[3];               // developer knob "eig_timing" = 2: fix-up rotations, full-sweep fallbacks, re-checks
+  __shared__ unsigned s_rot, s_dots;      // profiling (a.work != nullptr): applied rotations, column-pair dot products
 
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -228,6 +230,9 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
   }
 
   int sweeps = 0;
+  if (tid < 3) s_stat[tid] = 0;
+  if (tid == 0) { s_rot = 0u; s_dots = 0u; }
+
   float sigma = 0.f, trace = 0.f, wsum = 0.f;
   long long t_start = clock64(), t_sweeps0 = 0, t_sweeps1 = 0;
   for (int attempt = 0; attempt < 2; ++attempt) {
@@ -448,6 +453,7 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
           if (gl == 0) {
             nrm2[p] = fmaxf(fmaf(-t, ga, al), 0.f);
             nrm2[q] = fmaf(t, ga, be);
+            if (a.work != nullptr) atomicAdd(&s_rot, 1u);
           }
         }
       };
@@ -483,6 +489,7 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
         }
       }
       ++sweeps;
+      if (a.work != nullptr && tid == 0) s_dots += (unsigned)(D * (D - 1) / 2);
       wmax = warp_max(wmax);
       if (lane == 0) atomicMax(&s_flag, __float_as_uint(wmax));
       __syncthreads();
@@ -536,6 +543,7 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
           }
         }
         if (cmax > 0.f) atomicMax(&s_flag, __float_as_uint(cmax));
+        if (a.work != nullptr && tid == 0) s_dots += (unsigned)(D * (D - 1) / 2);
         __syncthreads();
         const float worst2 = __uint_as_float(s_flag);
         const bool more = worst2 > 0.f;
@@ -543,6 +551,10 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
         __syncthreads();
         if (tid == 0) { s_flag = 0u; s_nfix = 0u; }
         if (!more) { converged = true; break; }
+        if (tid == 0) {
+          if (nfix > (unsigned)MAXFIX || fixrounds >= 2) ++s_stat[1];
+          else { s_stat[0] += (int)nfix; s_stat[2] += fixrounds > 0 ? 1 : 0; }
+        }
         if (nfix > (unsigned)MAXFIX || fixrounds >= 2) { __syncthreads(); break; }   // full sweep
         // fix-up: one listed pair per round (they may share columns), in ascending (p, q) order so
         // that the result does not depend on the order in which the groups found them; every group
@@ -692,16 +704,24 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
     a.w[(size_t)b * D + i] = ev;
   }
   wsum -= (float)D * sigma;
+  if (a.work != nullptr && tid == 0) {
+    atomicAdd(a.work, (unsigned long long)s_dots);
+    atomicAdd(a.work + 1, (unsigned long long)s_rot);
+  }
   if (a.info && tid == 0) {
     float* o = a.info + (size_t)b * 4;
     o[0] = (float)sweeps;
     o[1] = sigma;
     o[2] = trace;
     o[3] = wsum;
-    if (a.timing) {  // developer knob "eig_timing": phase cycle counts instead of shift / trace / sum
+    if (a.timing == 1) {  // developer knob "eig_timing": phase cycle counts instead of shift / trace / sum
       o[1] = (float)(t_sweeps0 - t_start);
       o[2] = (float)(t_sweeps1 - t_sweeps0);
       o[3] = (float)(clock64() - t_sweeps1);
+    } else if (a.timing == 2) {  // convergence branches: fix-up rotations, full-sweep fallbacks, re-checks after a fix-up
+      o[1] = (float)s_stat[0];
+      o[2] = (float)s_stat[1];
+      o[3] = (float)s_stat[2];
     }
   }
   __syncthreads();
@@ -791,6 +811,7 @@ static int launch_cfg(const EigArgs& a, int B, size_t smem, cudaStream_t st) {
 int launch_eig_small(const EigArgs& a_in, int B, cudaStream_t st) {
   EigArgs a = a_in;
   a.timing = g_tune_timing;
+  a.work = profile_eig_counters();
   a.use_mma = g_tune_mma;
   a.ld = (a.D + 3) & ~3;
   if (a.D > UGLAD_SMALL_D_MAX) {

@@ -577,6 +577,57 @@ int launch_loss_terms(const float* theta, const float* S, long long strideS, con
 }
 
 // ------------------------------------------------------------------------------------------
+// Optional structure prior of main.py:325-334:  loss += sum log cosh(theta o mask) / Bdiv with
+// mask = (1 - struct_theta) - I, and its gradient tanh(theta o mask) o mask / Bdiv added to
+// grad_theta (may be NULL).  Same grid / partial layout as loss_terms_kernel, which has already
+// written loss_out[0]; the last block adds the prior to it (double accumulation).
+__global__ void __launch_bounds__(EW_THREADS) struct_prior_kernel(
+    const float* __restrict__ theta, const float* __restrict__ st, int D, float Bdiv, float* grad, float* part,
+    float* loss_out, unsigned* counter) {
+  __shared__ double redd[32];
+  __shared__ bool s_last;
+  const int b = blockIdx.y, nb = gridDim.x, B = gridDim.y, n = D * D;
+  const float* T = theta + (size_t)b * n;
+  const float* Sm = st + (size_t)b * n;
+  float* G = grad ? grad + (size_t)b * n : nullptr;
+  const float inv = 1.f / Bdiv;
+  double acc = 0.0;
+  for (int i = blockIdx.x * EW_THREADS + threadIdx.x; i < n; i += nb * EW_THREADS) {
+    const int r = i / D, c = i - r * D;
+    const float m = (1.f - Sm[i]) - ((r == c) ? 1.f : 0.f);
+    const float x = T[i] * m;
+    const float ax = fabsf(x);
+    acc += (double)ax + log1p(exp(-2.0 * (double)ax)) - 0.6931471805599453;   // log cosh x
+    if (G) G[i] = fmaf(tanhf(x) * m, inv, G[i]);
+  }
+  acc = block_sum_d(acc, redd);
+  if (threadIdx.x == 0) {
+    part[(size_t)b * nb + blockIdx.x] = (float)acc;
+    __threadfence();
+    const unsigned ticket = atomicAdd(counter, 1u);
+    s_last = (ticket == (unsigned)(nb * B) - 1u);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nb * B; i += EW_THREADS) s += (double)((volatile float*)part)[i];
+    s = block_sum_d(s, redd);
+    if (threadIdx.x == 0) {
+      loss_out[0] = (float)((double)loss_out[0] + s / (double)Bdiv);
+      *counter = 0u;
+    }
+  }
+}
+int launch_struct_prior(const float* theta, const float* struct_theta, int B, int D, float Bdiv, float* grad,
+                        float* part, float* loss_out, unsigned* counter, cudaStream_t st) {
+  dim3 grid(loss_blocks_per_graph(D), B);
+  struct_prior_kernel<<<grid, EW_THREADS, 0, st>>>(theta, struct_theta, D, Bdiv, grad, part, loss_out, counter);
+  UGLAD_CHECK_LAUNCH("struct_prior_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // covariance helpers
 // column means of X[B][M][D]: block (32 x 8), thread column = contiguous dimension
 __global__ void colmean_kernel(const float* __restrict__ X, int M, int D, float* mean) {
@@ -674,22 +725,76 @@ int launch_cov_reduce(const float* P, int B, int nch, int D, float* S, cudaStrea
 
 // prepare_data.py:348-350: if min eig <= 1e-6, S += (offset - min) I (and the eigenvalues move
 // by the same amount, the eigenvectors do not).  One block per graph.
-__global__ void condition_kernel(float* S, float* wS, int D, float offset) {
+// The reference takes the decision on float64 eigenvalues; the FP32 solver's eigenvalues carry
+// ~1e-6 ||S|| of error, which is the size of the threshold itself.  The smallest eigenvalue is
+// therefore refined first: the Rayleigh quotient u^T S u / u^T u of its FP32 eigenvector,
+// accumulated in double, is second-order accurate in the eigenvector error (~1e-10 ||S||), so the
+// decision and the shift (offset - min) only inherit the rounding of S itself.
+//
+// With the samples at hand (X != nullptr) the quotient is taken on the covariance of the samples
+// themselves, ||(X - mean) u||^2 / (M u^T u) in double, which is also free of the rounding of S
+// (the tensor-pipe covariance carries ~1e-6 ||S||).
+__global__ void condition_kernel(float* S, float* wS, const float* VtS, int D, float offset,
+                                 const float* __restrict__ X, const float* __restrict__ mean, int M) {
   __shared__ float red[32];
+  __shared__ double redd[32];
+  __shared__ int s_arg;
   const int b = blockIdx.x;
   float mn = INFINITY;
   for (int i = threadIdx.x; i < D; i += blockDim.x) mn = fminf(mn, wS[(size_t)b * D + i]);
   mn = -block_max(-mn, red);
-  if (mn <= 1e-6f) {
-    const float add = offset - mn;
+  if (threadIdx.x == 0) s_arg = D;
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x)
+    if (wS[(size_t)b * D + i] == mn) atomicMin(&s_arg, i);
+  __syncthreads();
+  double mnd = (double)mn;
+  if (VtS != nullptr && s_arg < D && X != nullptr) {
+    const float* u = VtS + (size_t)b * D * D + (size_t)s_arg * D;
+    const float* Xb = X + (size_t)b * M * D;
+    const float* mb = mean + (size_t)b * D;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double mu_u = 0.0, den = 0.0;
+    for (int d = lane; d < D; d += 32) {
+      mu_u += (double)mb[d] * (double)u[d];
+      den += (double)u[d] * (double)u[d];
+    }
+    mu_u = warp_sum_d(mu_u);
+    den = warp_sum_d(den);
+    double num = 0.0;
+    for (int m = warp; m < M; m += nw) {   // one sample per warp: y_m = (x_m - mean) . u
+      double y = 0.0;
+      for (int d = lane; d < D; d += 32) y += (double)Xb[(size_t)m * D + d] * (double)u[d];
+      y = warp_sum_d(y) - mu_u;
+      if (lane == 0) num += y * y;
+    }
+    num = block_sum_d(num, redd);
+    if (den > 0.0) mnd = num / ((double)M * den);
+  } else if (VtS != nullptr && s_arg < D) {
+    const float* u = VtS + (size_t)b * D * D + (size_t)s_arg * D;
+    const float* Sb = S + (size_t)b * D * D;
+    double num = 0.0, den = 0.0;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+      double row = 0.0;
+      for (int j = 0; j < D; ++j) row += (double)Sb[(size_t)i * D + j] * (double)u[j];
+      num += row * (double)u[i];
+      den += (double)u[i] * (double)u[i];
+    }
+    num = block_sum_d(num, redd);
+    den = block_sum_d(den, redd);
+    if (den > 0.0) mnd = num / den;
+  }
+  if (mnd <= 1e-6) {
+    const float add = (float)((double)offset - mnd);
     for (int i = threadIdx.x; i < D; i += blockDim.x) {
       wS[(size_t)b * D + i] += add;
       S[(size_t)b * D * D + (size_t)i * D + i] += add;
     }
   }
 }
-int launch_condition(float* S, float* wS, int B, int D, float offset, cudaStream_t st) {
-  condition_kernel<<<B, 256, 0, st>>>(S, wS, D, offset);
+int launch_condition(float* S, float* wS, const float* VtS, int B, int D, float offset, const float* X,
+                     const float* mean, int M, cudaStream_t st) {
+  condition_kernel<<<B, 256, 0, st>>>(S, wS, VtS, D, offset, (X && mean && M > 0) ? X : nullptr, mean, M);
   UGLAD_CHECK_LAUNCH("condition_kernel");
   return 0;
 }

@@ -814,7 +814,18 @@ void tc_forget_maps() {
   g_maps.clear();
 }
 
-static int g_num_sms = 0;
+// per-device caches (one process may drive several devices)
+constexpr int MAX_DEV = 64;
+static int g_num_sms_dev[MAX_DEV] = {0};
+static int num_sms(int* out) {
+  int dev = 0;
+  UGLAD_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= MAX_DEV) { set_error("device ordinal %d out of range", dev); return 1; }
+  if (g_num_sms_dev[dev] == 0)
+    UGLAD_CUDA(cudaDeviceGetAttribute(&g_num_sms_dev[dev], cudaDevAttrMultiProcessorCount, dev));
+  *out = g_num_sms_dev[dev];
+  return 0;
+}
 static int g_tc_bn = 0;   // 0 = auto
 static int g_tc_pdl = 1;  // programmatic dependent launch between the chained products
 int tc_tune_bn(int bn) { g_tc_bn = bn; return 0; }
@@ -841,11 +852,14 @@ static void fill_epi(TcEpi& e, const TcGemm& g) {
 template <int BN, bool RAW>
 static int launch_tc(const TcGemm& g, const TcGemm* g2, int batch, cudaStream_t st) {
   using C = tc::Cfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[MAX_DEV] = {false};   // the function attribute is per device
+  int dev = 0;
+  UGLAD_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= MAX_DEV) { set_error("device ordinal %d out of range", dev); return 1; }
+  if (!attr_set[dev]) {
     UGLAD_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     RAW ? C::SMEM_RAW : C::SMEM));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   CUtensorMap m[8];
   const TcGemm* gs[2] = {&g, g2 ? g2 : &g};
@@ -886,11 +900,8 @@ static int launch_tc(const TcGemm& g, const TcGemm* g2, int batch, cudaStream_t 
   fill_epi(p.e[0], g);
   fill_epi(p.e[1], *gs[1]);
   const long long total = (long long)p.tiles_m * p.tiles_n * batch * p.nprob;
-  if (g_num_sms == 0) {
-    int dev = 0;
-    UGLAD_CUDA(cudaGetDevice(&dev));
-    UGLAD_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int g_num_sms = 0;
+  if (num_sms(&g_num_sms)) return 1;
   const int grid = (int)(total < g_num_sms ? total : g_num_sms);
   profile_begin(st, 1, 2.0 * g.M * g.N * g.K * batch * p.nprob);
   cudaLaunchConfig_t cfg = {};
@@ -929,11 +940,8 @@ static int launch_tc_any(const TcGemm& g, const TcGemm* g2, int batch, cudaStrea
   }
   const bool raw = g.A_lo == nullptr;
   if (batch <= 0) return 0;
-  if (g_num_sms == 0) {
-    int dev = 0;
-    UGLAD_CUDA(cudaGetDevice(&dev));
-    UGLAD_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int g_num_sms = 0;
+  if (num_sms(&g_num_sms)) return 1;
   const int nprob = g2 ? 2 : 1;
   int bn = g_tc_bn;
   if (bn == 0) {

@@ -29,6 +29,7 @@ struct EigArgs {
   int max_sweeps = 40;
   int use_mma = 1;               // warm-start product / Rayleigh quotients via mma.sync (3xTF32)
   int timing = 0;                // developer knob: info[1..3] <- phase cycle counts
+  unsigned long long* work = nullptr;   // profiling: {column-pair dot products, applied rotations} accumulated over CTAs
   float tol = 1e-6f;   // cosine threshold.  2e-6 is 4 % faster and keeps theta within 1.8e-5 of the reference, but on the
                        // trained low-threshold golden it left an entry of 1.2e-5 where the reference has an exact zero
                        // (edge criterion: 1e-5); 1e-6 leaves 2e-6 there (scripts/gpu_edge_margin.py)
@@ -39,6 +40,7 @@ int launch_eig(const EigArgs& a, int B, cudaStream_t st);  // dispatch on D
 // optional CUDA-event bracket around the eigensolver launches (bench.py's roofline leg)
 void profile_begin(cudaStream_t st, int kind, double work);  // kind 0 eigensolver (bytes), 1 tcgen05 GEMM (flops)
 void profile_end(cudaStream_t st);
+unsigned long long* profile_eig_counters();   // device {dots, rotations} while profiling is on, else nullptr
 size_t eig_scratch_floats(int B, int D);
 
 // ---- batched SGEMM ------------------------------------------------------------------------
@@ -124,6 +126,11 @@ size_t chol_scratch_floats(int B, int D);
 int chol_factor(float* A, int B, int D, float shift, const float* shift_dev, float* logdet, float* scratch,
                 cudaStream_t st);
 const int* chol_fail_flags(float* scratch, int B, int D);
+int chol_pd_test_f64(const float* S, const double* S64, int B, int D, const double* shift_dev, const int* active_dev,
+                     double* work, int* fail_dev, cudaStream_t st);
+int launch_cov_f64(const float* X, const float* mean, int B, int M, int D, const int* active_dev, double* S64,
+                   cudaStream_t st);
+int launch_trace(const float* S, int B, int D, float* out, cudaStream_t st);
 int chol_inverse(const float* Lf, int B, int D, float* W, float* Ainv, float alpha, const float* E1,
                  long long sE1, float beta, float* scratch, cudaStream_t st);
 int launch_copy_shift(const float* src, long long sSrc, int B, int D, float shift, const float* shift_dev,
@@ -164,10 +171,13 @@ int loss_blocks_per_graph(int D);
 int launch_loss_terms(const float* theta, const float* S, long long strideS, const float* logdet,
                       int B, int D, float Bdiv, float* part, float* lossb, float* loss_out, unsigned* counter,
                       cudaStream_t st);
+int launch_struct_prior(const float* theta, const float* struct_theta, int B, int D, float Bdiv, float* grad,
+                        float* part, float* loss_out, unsigned* counter, cudaStream_t st);
 int launch_colmean(const float* X, int B, int M, int D, float* mean, cudaStream_t st);
 int launch_center_transpose(const float* X, const float* mean, int B, int M, int D, int kc, int nch, float* Xt,
                             cudaStream_t st);
 int launch_cov_reduce(const float* P, int B, int nch, int D, float* S, cudaStream_t st);
-int launch_condition(float* S, float* wS, int B, int D, float offset, cudaStream_t st);
+int launch_condition(float* S, float* wS, const float* VtS, int B, int D, float offset, const float* X,
+                     const float* mean, int M, cudaStream_t st);
 
 }  // namespace uglad

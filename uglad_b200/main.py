@@ -31,17 +31,16 @@ def init_uGLAD(lr: float, theta_init_offset: float = 1.0, nF: int = 3, H: int = 
 
 
 def loss_uGLAD(theta: torch.Tensor, S: torch.Tensor, struct_theta: Optional[torch.Tensor] = None,
-               group=None, total_graphs: Optional[int] = None) -> torch.Tensor:
+               group=None, total_graphs: Optional[int] = None, replicated_S: bool = False) -> torch.Tensor:
     """main.py:289-335: sum_b(-logdet theta_b + <S_b, theta_b>) / B with B = S.shape[0]
     (the number of graphs over all processes when `group` shards them), plus the optional
     log-cosh structure prior."""
-    B = int(total_graphs) if total_graphs is not None else ops.global_graph_count(S.shape[0], S.device, group)
-    loss = ops.GlassoLossFunction.apply(theta, S, float(B))
-    if struct_theta is not None:
-        D = S.shape[-1]
-        mask = (1 - struct_theta) - torch.eye(D, device=theta.device).expand(S.shape[0], -1, -1)
-        loss = loss + torch.sum(torch.log(torch.cosh(theta * mask))) / B
-    return loss
+    if replicated_S or (group is None and total_graphs is None):
+        B = S.shape[0]   # the reference's divisor (main.py:303); a replicated S (the broadcast full-data covariance of
+                         # the consensus mode, main.py:620-622) is not sharded, so its count is not summed over ranks
+    else:
+        B = int(total_graphs) if total_graphs is not None else ops.global_graph_count(S.shape[0], S.device, group)
+    return ops.GlassoLossFunction.apply(theta, S, float(B), struct_theta)
 
 
 def forward_uGLAD(Sb, model_glad, L: int = 15, INIT_DIAG: int = 0, loss_Sb=None, struct_theta=None,
@@ -51,7 +50,7 @@ def forward_uGLAD(Sb, model_glad, L: int = 15, INIT_DIAG: int = 0, loss_Sb=None,
     all-reduce of every call when the caller already knows it."""
     predTheta = glad.glad(Sb, model_glad, L=L, INIT_DIAG=INIT_DIAG, group=group, total_graphs=total_graphs)
     loss = loss_uGLAD(predTheta, Sb if loss_Sb is None else loss_Sb, struct_theta=struct_theta, group=group,
-                      total_graphs=total_graphs)
+                      total_graphs=total_graphs, replicated_S=loss_Sb is not None)
     return predTheta, loss
 
 
@@ -67,15 +66,27 @@ def _fit_loop(Sb, model, optimizer, EPOCHS, L, INIT_DIAG, VERBOSE, loss_Sb=None,
         optimizer.zero_grad()
         predTheta, loss = forward_uGLAD(Sb, model, L=L, INIT_DIAG=INIT_DIAG, loss_Sb=loss_Sb,
                                         struct_theta=struct_theta, group=group, total_graphs=total)
-        if stop_on_nan and bool(torch.isnan(loss)):
+        shown = loss.detach()
+        if group is not None and (stop_on_nan or (VERBOSE and not e % every)):
+            # each rank holds the loss of its own graphs (already divided by the global count): the
+            # reported value and the NaN stop must be the same on every rank
+            shown = ops.allreduce_sum(shown.clone().reshape(1), group)[0]
+        if stop_on_nan and bool(torch.isnan(shown)):
             print(f"Warning: NaN loss encountered at epoch {e}. Try updating the parameters and train.")
             break
         loss.backward()
         if VERBOSE and not e % every:
-            print(f"{tag}epoch:{e}/{EPOCHS} loss:{loss.item()}")
+            print(f"{tag}epoch:{e}/{EPOCHS} loss:{shown.item()}")
         optimizer.step()
-        losses.append(loss.detach())
+        losses.append(shown)
     return predTheta, losses
+
+
+def _share_model(model, group):
+    """One model over all ranks: rank 0's initialisation everywhere."""
+    import torch.distributed as dist
+    for p in model.parameters():
+        dist.broadcast(p.data, src=dist.get_global_rank(group, 0), group=group)
 
 
 def _compare(trueTheta, predTheta, b=0):
@@ -154,42 +165,80 @@ def mean_imputation(Xb: np.ndarray) -> np.ndarray:
     return np.expand_dims(X, axis=0)
 
 
-def get_final_precision_from_batch(predTheta: torch.Tensor, type: str = "min") -> torch.Tensor:
+def get_final_precision_from_batch(predTheta: torch.Tensor, type: str = "min", group=None) -> torch.Tensor:
     """main.py:673-716: consensus over K precision matrices: majority sign (ties -> +) times
-    the min (or mean) magnitude."""
+    the min (or mean) magnitude.  With `group` the K matrices are sharded over the ranks: the
+    local min |theta| / sum sign(theta) are combined by one all-reduce(MIN) and one all-reduce(SUM)
+    (both exact in floating point, so N ranks reproduce the single-process result bit for bit)."""
     K, _, D = predTheta.shape
     mag = torch.abs(predTheta)
+    votes = torch.sum(torch.sign(predTheta), 0)
     if type == "min":
         value = torch.min(mag, 0)[0]
+        if group is not None:
+            value = ops.allreduce_min(value.contiguous(), group)
     elif type == "mean":
+        if group is not None:
+            raise NotImplementedError("sharded consensus implements type='min' (the reference's setting, main.py:632)")
         value = torch.mean(mag, 0)[0]  # sic: the reference indexes the mean too (main.py:705)
     else:
         print(f"Enter valid type min/mean, currently {type}")
         sys.exit(0)
-    votes = torch.sum(torch.sign(predTheta), 0)
+    if group is not None:
+        votes = ops.allreduce_sum(votes.contiguous(), group)   # sums of +-1/0: exact
     sign = torch.where(votes >= 0, torch.ones_like(votes), -torch.ones_like(votes))
     return (sign * value).reshape(1, D, D)
 
 
+def kfold_train_indices(M: int, K: int):
+    """Row indices of the K training folds of sklearn's KFold(n_splits=K) without shuffling (the
+    reference's row-subsampled batches, main.py:604-606): fold k drops one contiguous block of
+    M // K (+1 for the first M % K folds) rows."""
+    sizes = np.full(K, M // K, dtype=np.int64)
+    sizes[: M % K] += 1
+    stops = np.cumsum(sizes)
+    rows = np.arange(M)
+    return [np.concatenate([rows[: stop - size], rows[stop:]]) for size, stop in zip(sizes, stops)]
+
+
+def consensus_covariances(X: torch.Tensor, K_batch: int, eval_offset: float = 0.1, group=None, warm=None):
+    """main.py:598-610 on the device: X [M, D] (imputed samples, CUDA) -> (S_K, Sb): the covariances
+    of this rank's share of the K row-subsampled batches and the full-data covariance [1, D, D].
+    The sub-samples are gathered on the device and go through the batched covariance kernels (two
+    launches: the folds come in at most two sizes)."""
+    M = X.shape[0]
+    folds = kfold_train_indices(M, K_batch)
+    mine = range(K_batch)
+    if group is not None:
+        import torch.distributed as dist
+        mine = np.array_split(np.arange(K_batch), dist.get_world_size(group))[dist.get_rank(group)]
+    X_K = [X[torch.as_tensor(folds[k], device=X.device)] for k in mine]
+    w_full, w_K = (warm if warm is not None else (None, None))
+    Sb = prepare_data.get_covariance(X.unsqueeze(0), offset=eval_offset, warm=w_full)
+    S_K = prepare_data.get_covariance(X_K, offset=eval_offset, warm=w_K)
+    return S_K, Sb
+
+
 def run_uGLAD_missing(Xb, trueTheta=None, eval_offset=0.1, EPOCHS=250, lr=0.002, INIT_DIAG=0, L=15,
-                      VERBOSE=True, K_batch=3):
+                      VERBOSE=True, K_batch=3, group=None):
     """main.py:553-644: mean-impute, build K row-subsampled covariances (the training folds of
     a K-fold split), fit one model on all K with the full-data covariance in the loss, then
-    take the consensus."""
-    from sklearn.model_selection import KFold
+    take the consensus.  With `group` the K imputations are sharded over the ranks (every rank
+    passes the same Xb): the model is shared exactly as in the multitask mode and the consensus
+    is reduced across ranks."""
     if K_batch == 0:
         K_batch = 3
     Xb = mean_imputation(np.array(Xb, dtype=np.float64))
-    Sb = prepare_data.get_covariance(Xb, offset=eval_offset)
     print(f"Creating K={K_batch} row-subsampled batches")
-    X_K = [Xb[0][idx] for idx, _ in KFold(n_splits=K_batch).split(Xb[0])]
-    S_K = prepare_data.get_covariance(X_K, offset=eval_offset)
+    S_K, Sb = consensus_covariances(prepare_data.convert_to_torch(Xb[0]), K_batch, eval_offset, group)
     if trueTheta is not None:
         trueTheta = prepare_data.convert_to_torch(trueTheta, req_grad=False)
     model_glad, optimizer_glad = init_uGLAD(lr=lr, theta_init_offset=1.0, nF=3, H=3)
-    predTheta, _ = _fit_loop(S_K, model_glad, optimizer_glad, EPOCHS, L, INIT_DIAG, VERBOSE, loss_Sb=Sb)
+    if group is not None:
+        _share_model(model_glad, group)
+    predTheta, _ = _fit_loop(S_K, model_glad, optimizer_glad, EPOCHS, L, INIT_DIAG, VERBOSE, loss_Sb=Sb, group=group)
     print("Getting the final precision matrix using the consensus strategy")
-    predTheta = get_final_precision_from_batch(predTheta.detach(), type="min")
+    predTheta = get_final_precision_from_batch(predTheta.detach(), type="min", group=group)
     compare_theta = None
     if trueTheta is not None:
         compare_theta = _compare(trueTheta, predTheta, 0)
@@ -207,9 +256,7 @@ def run_uGLAD_multitask(Xb, trueTheta=None, eval_offset=0.1, EPOCHS=250, lr=0.00
         trueTheta = prepare_data.convert_to_torch(trueTheta, req_grad=False)
     model_glad, optimizer_glad = init_uGLAD(lr=lr, theta_init_offset=1.0, nF=3, H=3)
     if group is not None:
-        import torch.distributed as dist
-        for p in model_glad.parameters():  # one model: rank 0's initialisation everywhere
-            dist.broadcast(p.data, src=dist.get_global_rank(group, 0), group=group)
+        _share_model(model_glad, group)
     predTheta, _ = _fit_loop(Sb, model_glad, optimizer_glad, EPOCHS, L, INIT_DIAG, VERBOSE, group=group)
     compare_theta = []
     if trueTheta is not None:

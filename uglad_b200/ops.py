@@ -28,7 +28,7 @@ def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
     return t.contiguous()
 
 
-def covariance(X: torch.Tensor) -> torch.Tensor:
+def covariance(X: torch.Tensor, return_mean: bool = False):
     """S[b] = (X_b - mean)^T (X_b - mean) / M for X [B,M,D] (prepare_data.py:342-344)."""
     X = _f32c(X, "X")
     if X.dim() == 2:
@@ -40,7 +40,7 @@ def covariance(X: torch.Tensor) -> torch.Tensor:
     # the contraction runs on the tensor pipe (tcgen05 3xTF32) from centred, feature-major samples in scratch
     scratch = torch.empty(max(lib.uglad_covariance_scratch_floats(B, M, D), 1), device=X.device, dtype=torch.float32)
     check(lib.uglad_covariance_ws(_ptr(X), B, M, D, _ptr(S), _ptr(mean), _ptr(scratch), _stream(X)), "uglad_covariance_ws")
-    return S
+    return (S, mean) if return_mean else S
 
 
 def eigh(A: torch.Tensor, indefinite: bool = True) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
@@ -63,20 +63,29 @@ class ConditionedCovariance:
     """S after the eigenvalue repair of prepare_data.py:345-355 plus its eigendecomposition,
     which every forward reuses for theta_0 = (S + t I)^-1 (glad.py:115-117)."""
 
-    def __init__(self, S: torch.Tensor, offset: float = 0.1, repair: bool = True, warm=None):
+    def __init__(self, S: torch.Tensor, offset: float = 0.1, repair: bool = True, warm=None, X=None, mean=None):
         """`warm`: an earlier ConditionedCovariance of the same shape (e.g. the previous batch of a
-        stream of similar sample matrices); its eigenvectors seed the solver."""
+        stream of similar sample matrices); its eigenvectors seed the solver.  `X` [B,M,D] / `mean`
+        [B,D]: the samples S was computed from; with them the repair decision is taken on the
+        float64 covariance of the samples, as the reference does (uglad_condition_covariance_x)."""
         S = _f32c(S, "S").clone()
         B, D, _ = S.shape
         lib = _lib.load()
         self.S = S
+        M = 0
+        if X is not None and mean is not None:
+            X, mean = _f32c(X, "X"), _f32c(mean, "mean")
+            M = X.shape[1]
+        else:
+            X = mean = None
         if D > lib.uglad_small_d_max():
             # large-D path: no eigendecomposition is kept (theta_0 comes from a Cholesky inverse)
             self.wS = self.VtS = self.info = None
             if repair:
                 scratch = torch.empty(lib.uglad_condition_scratch_floats(B, D), device=S.device, dtype=torch.float32)
-                check(lib.uglad_condition_covariance(_ptr(S), B, D, float(offset), None, None, None, _ptr(scratch),
-                                                     _stream(S)), "uglad_condition_covariance")
+                check(lib.uglad_condition_covariance_x(_ptr(S), _ptr(X), _ptr(mean), B, M, D, float(offset), None, None,
+                                                       None, _ptr(scratch), None, None, _stream(S)),
+                      "uglad_condition_covariance")
             return
         self.wS = torch.empty(B, D, device=S.device, dtype=torch.float32)
         self.VtS = torch.empty(B, D, D, device=S.device, dtype=torch.float32)
@@ -87,9 +96,9 @@ class ConditionedCovariance:
         if warm is not None and warm.VtS is not None and warm.VtS.shape == self.VtS.shape:
             wV, ww = warm.VtS, warm.wS
         if repair:
-            check(lib.uglad_condition_covariance_warm(_ptr(S), B, D, float(offset), _ptr(self.wS), _ptr(self.VtS),
-                                                      _ptr(self.info), _ptr(scratch), _ptr(wV), _ptr(ww), _stream(S)),
-                  "uglad_condition_covariance")
+            check(lib.uglad_condition_covariance_x(_ptr(S), _ptr(X), _ptr(mean), B, M, D, float(offset), _ptr(self.wS),
+                                                   _ptr(self.VtS), _ptr(self.info), _ptr(scratch), _ptr(wV), _ptr(ww),
+                                                   _stream(S)), "uglad_condition_covariance")
         else:
             check(lib.uglad_eigh_warm(_ptr(S), B, D, 1, _ptr(self.wS), _ptr(self.VtS), _ptr(self.info),
                                       _ptr(scratch), _ptr(wV), _ptr(ww), _stream(S)), "uglad_eigh")
@@ -115,17 +124,44 @@ def make_dims(B, D, L, H, init_diag, B_total=None, exact_sqrt=False, lambda_init
                      int(bool(exact_sqrt)), float(lambda_init))
 
 
-_warm: dict = {}
+# Warm start of the per-layer eigensolver: the workspace of an earlier forward seeds the next one.
+# Keyed by problem shape + workspace layout AND by the covariance tensor it was computed for, so
+# that alternating inputs of one shape (the train / test covariances of the CV mode, main.py:486-494)
+# each continue from their own previous epoch.  A forward on a tensor never seen before falls back
+# to the most recent workspace of the same shape (fresh data of a stream: a valid, if weaker, seed --
+# a warm start changes the work done, never the converged result).
+import collections
+
+_warm: "collections.OrderedDict" = collections.OrderedDict()
+_WARM_MAX = 3
 warm_start_enabled = True
 
 
 def reset_warm_start():
-    """Forget the eigenvector seed (the next forward solves from scratch)."""
+    """Forget the eigenvector seeds (the next forward solves from scratch)."""
     _warm.clear()
+
+
+def _warm_lookup(shape_key, tensor_key):
+    hit = _warm.get((shape_key, tensor_key))
+    if hit is not None:
+        return hit
+    for (sk, _), ws in reversed(_warm.items()):
+        if sk == shape_key:
+            return ws
+    return None
+
+
+def _warm_store(shape_key, tensor_key, ws):
+    _warm.pop((shape_key, tensor_key), None)
+    _warm[(shape_key, tensor_key)] = ws
+    while len(_warm) > _WARM_MAX:
+        _warm.popitem(last=False)
 
 
 def tune(key: str, value: int):
     check(_lib.load().uglad_tune(key.encode(), int(value)), "uglad_tune")
+    _warm.clear()   # a knob may change the workspace layout ("small_d_max") or the solver's state
 
 
 # ---- graph-sharded execution (one process per GPU) ------------------------------------------------
@@ -163,6 +199,18 @@ def allreduce_shared_gradients(gp: torch.Tensor, group) -> torch.Tensor:
     return gp
 
 
+def allreduce_sum(t: torch.Tensor, group) -> torch.Tensor:
+    import torch.distributed as dist
+    dist.all_reduce(t, group=group)
+    return t
+
+
+def allreduce_min(t: torch.Tensor, group) -> torch.Tensor:
+    import torch.distributed as dist
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return t
+
+
 class GladFunction(torch.autograd.Function):
     """theta_pred = glad(S; params)  (glad.py:74-150) with the hand-written backward."""
 
@@ -187,8 +235,9 @@ class GladFunction(torch.autograd.Function):
         ws = torch.empty(n, device=S.device, dtype=torch.float32)
         # warm start: the previous forward's workspace for the same problem shape (normally the
         # previous epoch of the same fit) seeds the eigensolver; see uglad_glad_forward.
-        wkey = (B, D, L, H, init_diag, S.device.index)
-        warm = _warm.get(wkey) if warm_start_enabled else None
+        wkey = (B, D, L, H, init_diag, S.device.index, lib.uglad_small_d_max(), n)
+        tkey = getattr(S, "_uglad_warm_key", None) or (S.data_ptr(), S._version)
+        warm = _warm_lookup(wkey, tkey) if warm_start_enabled else None
         eig = _eig_of(S) if (init_diag == 0 and D <= lib.uglad_small_d_max()) else None
         wS, VtS = (eig.wS, eig.VtS) if eig is not None else (None, None)
         st = _stream(S)
@@ -206,8 +255,7 @@ class GladFunction(torch.autograd.Function):
 
             run_sharded_layers(L, layer, ws[off:off + L], group)
         if warm_start_enabled:
-            _warm.clear()  # keep exactly one earlier workspace alive
-            _warm[wkey] = ws
+            _warm_store(wkey, tkey, ws)
         off = lib.uglad_workspace_offset(C.byref(dims), b"theta")
         theta = ws[off:off + B * D * D].view(B, D, D)
         ctx.dims, ctx.ws, ctx.S, ctx.params, ctx.eig, ctx.group, ctx.world = dims, ws, S, flat_params, eig, group, world
@@ -231,24 +279,26 @@ class GlassoLossFunction(torch.autograd.Function):
     """loss = sum_b(-logdet theta_b + <S_b, theta_b>) / Bdiv  (main.py:306-315)."""
 
     @staticmethod
-    def forward(ctx, theta, S, Bdiv):
+    def forward(ctx, theta, S, Bdiv, struct_theta=None):
         lib = _lib.load()
         theta = _f32c(theta, "theta")
         S = _f32c(S, "S")
+        if struct_theta is not None:   # log-cosh structure prior (main.py:325-334), one mask per graph
+            struct_theta = _f32c(struct_theta, "struct_theta").expand(theta.shape).contiguous()
         B, D, _ = theta.shape
         sb = S.shape[0]
         loss = torch.empty(1, device=theta.device, dtype=torch.float32)
         need_grad = ctx.needs_input_grad[0]
         grad = torch.empty_like(theta) if need_grad else None
         scratch = torch.empty(lib.uglad_loss_scratch_floats(B, D), device=theta.device, dtype=torch.float32)
-        check(lib.uglad_glasso_loss(_ptr(theta), _ptr(S), B, D, sb, float(Bdiv), _ptr(loss), _ptr(grad),
-                                    _ptr(scratch), _stream(theta)), "uglad_glasso_loss")
+        check(lib.uglad_glasso_loss_prior(_ptr(theta), _ptr(S), _ptr(struct_theta), B, D, sb, float(Bdiv), _ptr(loss),
+                                          _ptr(grad), _ptr(scratch), _stream(theta)), "uglad_glasso_loss")
         ctx.grad = grad
         return loss[0]
 
     @staticmethod
     def backward(ctx, gout):
-        return ctx.grad * gout, None, None
+        return ctx.grad * gout, None, None, None
 
 
 def z_update(X, S, theta_prev, flat_params, H=3):

@@ -33,20 +33,30 @@ def get_covariance(Xb, offset: float = 0.1, warm=None) -> torch.Tensor:
     tensor [B,D,D] with their eigendecomposition attached for glad()'s theta_0.  `warm`: the
     result of an earlier call on similar data (same shapes); it seeds the eigensolver."""
     dev = _device()
+    wcc = getattr(warm, "_uglad_eig", (None, None))[1] if warm is not None else None
     if torch.is_tensor(Xb) or (isinstance(Xb, np.ndarray) and Xb.ndim == 3):
         X = convert_to_torch(Xb)
-        S = ops.covariance(X)
-    else:  # ragged list: group equal shapes so that each group is one batched launch
-        mats = [np.asarray(x, dtype=np.float32) for x in Xb]
-        S = torch.empty(len(mats), mats[0].shape[1], mats[0].shape[1], device=dev)
+        S, mean = ops.covariance(X, return_mean=True)
+        cc = ops.ConditionedCovariance(S, offset=offset, repair=True, warm=wcc, X=X, mean=mean)
+    else:  # ragged list (arrays or device tensors): equal shapes are grouped into one batched launch each
+        mats = [convert_to_torch(x) for x in Xb]
         shapes = {}
         for i, m in enumerate(mats):
-            shapes.setdefault(m.shape, []).append(i)
+            shapes.setdefault(tuple(m.shape), []).append(i)
+        parts = []
         for shp, idx in shapes.items():
-            X = torch.from_numpy(np.stack([mats[i] for i in idx])).to(dev)
-            S[idx] = ops.covariance(X)
-    wcc = getattr(warm, "_uglad_eig", (None, None))[1] if warm is not None else None
-    cc = ops.ConditionedCovariance(S, offset=offset, repair=True, warm=wcc)
+            X = torch.stack([mats[i] for i in idx])
+            S, mean = ops.covariance(X, return_mean=True)
+            parts.append((idx, ops.ConditionedCovariance(S, offset=offset, repair=True, X=X, mean=mean)))
+        if len(parts) == 1 and parts[0][0] == list(range(len(mats))):
+            cc = parts[0][1]
+        else:  # stitch the groups back into input order
+            cc = ops.ConditionedCovariance.__new__(ops.ConditionedCovariance)
+            order = torch.empty(len(mats), dtype=torch.long, device=dev)
+            order[torch.as_tensor([i for idx, _ in parts for i in idx], device=dev)] = torch.arange(len(mats), device=dev)
+            cat = lambda name: (None if getattr(parts[0][1], name) is None
+                                else torch.cat([getattr(p, name) for _, p in parts])[order].contiguous())
+            cc.S, cc.wS, cc.VtS, cc.info = cat("S"), cat("wS"), cat("VtS"), cat("info")
     out = cc.S
     out._uglad_eig = (out._version, cc)
     return out
@@ -61,9 +71,12 @@ class CovariancePrefetcher:
         for each step:  S = pf.get(); loss = step(S); pf.submit(X_next_pinned); loss.item()
 
     Everything is staged in three rotating, preallocated slots (no allocator traffic on the side
-    stream, which would otherwise synchronise the device now and then): the tensor returned by
-    get() is overwritten three submits later.  Consecutive batches seed each other's eigensolver
-    (a warm start changes the work, never the result)."""
+    stream, which would otherwise synchronise the device now and then).  The tensor returned by
+    get() stays valid until the NEXT get(): at that point the work the consumer has enqueued on it
+    is fenced by an event, and the side stream waits for that event before it overwrites the slot
+    three submits later -- so the host may run any number of steps ahead of the device.
+    Consecutive batches seed each other's eigensolver (a warm start changes the work, never the
+    result)."""
 
     SLOTS = 3
 
@@ -74,6 +87,7 @@ class CovariancePrefetcher:
         self._slots = None
         self._n = 0
         self._pending = None
+        self._handed = None   # the slot the consumer is working on (released at the next get())
 
     def _make_slots(self, shape):
         import ctypes as C
@@ -87,7 +101,7 @@ class CovariancePrefetcher:
             sl = {"X": torch.empty(B, M, D, **f), "S": torch.empty(B, D, D, **f), "mean": torch.empty(B, D, **f),
                   "Xt": torch.empty(max(lib.uglad_covariance_scratch_floats(B, M, D), 1), **f),
                   "scratch": torch.empty(max(lib.uglad_condition_scratch_floats(B, D), 1), **f),
-                  "ev": torch.cuda.Event()}
+                  "ev": torch.cuda.Event(), "released": None}
             cc = ops.ConditionedCovariance.__new__(ops.ConditionedCovariance)
             cc.S = sl["S"]
             if large:
@@ -106,7 +120,14 @@ class CovariancePrefetcher:
             X_host = X_host.unsqueeze(0)
         if self._slots is None or tuple(self._slots[0]["X"].shape) != tuple(X_host.shape):
             self._slots, self._n = self._make_slots(tuple(X_host.shape)), 0
+            self._handed = None
+            # the slots were just carved out of the caching allocator on the consumer's stream: a recycled
+            # block may still be read by kernels queued there
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
         sl = self._slots[self._n % self.SLOTS]
+        if sl["released"] is not None:   # the consumer's work on this slot's previous content
+            self.stream.wait_event(sl["released"])
+            sl["released"] = None
         prev = self._slots[(self._n - 1) % self.SLOTS]["cc"] if self._n > 0 else None
         self._n += 1
         B, M, D = sl["X"].shape
@@ -118,17 +139,24 @@ class CovariancePrefetcher:
                       "uglad_covariance_ws")
             cc = sl["cc"]
             wV, ww = (prev.VtS, prev.wS) if (prev is not None and prev.VtS is not None) else (None, None)
-            ops.check(lib.uglad_condition_covariance_warm(P(sl["S"]), B, D, self.offset, P(cc.wS), P(cc.VtS),
-                                                          P(cc.info), P(sl["scratch"]), P(wV), P(ww), st),
+            ops.check(lib.uglad_condition_covariance_x(P(sl["S"]), P(sl["X"]), P(sl["mean"]), B, M, D, self.offset,
+                                                       P(cc.wS), P(cc.VtS), P(cc.info), P(sl["scratch"]), P(wV), P(ww), st),
                       "uglad_condition_covariance")
             sl["ev"].record(self.stream)
         self._pending = sl
 
     def get(self) -> torch.Tensor:
         sl, self._pending = self._pending, None
-        torch.cuda.current_stream(self.device).wait_event(sl["ev"])
+        cur = torch.cuda.current_stream(self.device)
+        if self._handed is not None:   # everything enqueued so far on the slot handed out before
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self._handed["released"] = ev
+        self._handed = sl
+        cur.wait_event(sl["ev"])
         S = sl["S"]
         S._uglad_eig = (S._version, sl["cc"])
+        S._uglad_warm_key = ("prefetch", id(self))   # consecutive batches of one stream seed each other (ops._warm)
         return S
 
 
@@ -141,11 +169,41 @@ def normalize_table(df, typeN: str):
     return df
 
 
+def _cov_spectrum(values: np.ndarray):
+    """prepare_data.py:310-325, :568-594: biased covariance of a sample table, its eigenvalues (real
+    parts) and the condition number max|eig| / min|eig|."""
+    X = np.asarray(values, dtype=np.float64)
+    Xc = X - X.mean(axis=0)
+    S = Xc.T @ Xc / X.shape[0]
+    eig = np.linalg.eigvals(S).real
+    with np.errstate(divide="ignore"):
+        con = np.abs(eig).max() / np.abs(eig).min()
+    return S, eig, con
+
+
+def get_highly_correlated_features(input_cov: np.ndarray) -> np.ndarray:
+    """prepare_data.py:519-549: rank the features by how many strong second-order correlations they
+    have.  The covariance matrix's rows are treated as samples; entries of that second covariance
+    (diagonal zeroed) at or above the value ranked 10 % from the top of the upper triangle count as
+    strong; features are returned by decreasing number of strong partners (ties keep index order)."""
+    C = np.asarray(input_cov, dtype=np.float64)
+    Cc = C - C.mean(axis=0)
+    cov2 = Cc.T @ Cc / C.shape[0]
+    np.fill_diagonal(cov2, 0.0)
+    mag = np.abs(cov2)
+    upper = np.sort(mag[np.triu_indices(mag.shape[0], 1)])[::-1]
+    th = upper[int(0.1 * upper.size)]
+    rows = np.nonzero(mag >= th)[0]
+    feats, counts = np.unique(rows, return_counts=True)
+    return feats[np.argsort(-counts, kind="stable")]
+
+
 def process_table(table, NORM: str = "no", MIN_VARIANCE: float = 0.0, msg: str = "",
                   COND_NUM: float = np.inf, eigval_th: float = 1e-3, VERBOSE: bool = True):
-    """Drop all-zero rows, mean-impute NaNs, drop constant and duplicate columns, normalise,
-    drop columns whose variance is below MIN_VARIANCE.  (The reference's optional
-    condition-number pruning loop only runs for a finite COND_NUM, which fit() never passes.)"""
+    """prepare_data.py:361-516: drop all-zero rows, mean-impute NaNs, drop constant and duplicate
+    columns, normalise, drop columns whose variance is below MIN_VARIANCE; then, while the
+    covariance's condition number exceeds COND_NUM, drop the most inter-correlated features -- as
+    many as there are eigenvalues below eigval_th (at least one) per pass."""
     import pandas as pd
     table = pd.DataFrame(table).astype(float)
     table = table.loc[~(table == 0).all(axis=1)]
@@ -157,7 +215,17 @@ def process_table(table, NORM: str = "no", MIN_VARIANCE: float = 0.0, msg: str =
     var = table.var()
     table = table.drop(columns=list(var[var < MIN_VARIANCE].index))
     if COND_NUM != np.inf:
-        raise NotImplementedError("condition-number pruning (COND_NUM < inf) is outside the hot path")
+        S, eig, con = _cov_spectrum(table.values)
+        itr = 1
+        while con > COND_NUM:
+            n_small = int(np.sum(eig < eigval_th)) or 1   # still ill-conditioned with no small eigenvalue: drop one
+            ranked = get_highly_correlated_features(S)
+            drop = table.columns[ranked[: min(n_small, len(ranked))]]
+            if VERBOSE:
+                print(f"{msg} {itr}: condition number {con}: dropping {len(drop)} highly correlated features {list(drop)}")
+            table = table.drop(columns=drop)
+            S, eig, con = _cov_spectrum(table.values)
+            itr += 1
     if VERBOSE:
         print(f"{msg}: processed table has {table.shape[0]} samples and {table.shape[1]} features")
     return table
