@@ -150,13 +150,20 @@ def cpu_reference_rate(name, steps, warmup, max_graphs=None):
     vendored copy is absent.  `max_graphs` bounds the sample (None: the whole workload)."""
     import torch
     from oracle import ref_loader
+    spec = WORKLOADS[name]
+    B, D, M = spec["B"], spec["D"], spec["M"]
+    nb = B if max_graphs is None else min(B, max_graphs)
+    threads_note = ""
     try:  # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it may
         torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
     except Exception:
         pass
-    spec = WORKLOADS[name]
-    B, D, M = spec["B"], spec["D"], spec["M"]
-    nb = B if max_graphs is None else min(B, max_graphs)
+    if nb > 1 and D > 128:
+        # torch 2.11's batched CPU LU (the reference's torch.inverse / torch.logdet on [B, D, D]) is broken in
+        # this image on more than one thread for D > 128 (oneMKL SLASWP parameter error, then garbage or a hang:
+        # profiles/r02_torch_cpu_batched_lu_bug.txt).  The unmodified reference can only run this shape on 1 thread.
+        torch.set_num_threads(1)
+        threads_note = "; 1 thread: torch's batched CPU LU is broken multi-threaded for D > 128 in this image"
     ref = ref_loader.load()
     kind = "reference" if ref is not None else "port"
     if ref is not None:
@@ -206,7 +213,7 @@ def cpu_reference_rate(name, steps, warmup, max_graphs=None):
     dt = time.perf_counter() - t0
     what = ("the reference itself (oracle/_ref: uglad.main.forward_uGLAD + Adam, per-matrix Newton-Schulz loop)"
             if kind == "reference" else "oracle port (torch CPU restatement, batched)")
-    sample = f"{nb} of {B} graphs per step, {steps} timed steps after {warmup} warm-up; {what}"
+    sample = f"{nb} of {B} graphs per step, {steps} timed steps after {warmup} warm-up; {what}{threads_note}"
     return dict(value=nb * L_LAYERS * steps / dt, ms_per_step=dt / steps * 1e3, graphs=nb,
                 cores=torch.get_num_threads(), kind=kind, sample=sample)
 

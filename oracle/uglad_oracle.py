@@ -130,6 +130,17 @@ def ns_sqrt(A: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------------------
 # unrolled GLAD + loss  (matmul formulation)
 # --------------------------------------------------------------------------------------
+def _per_matrix(fn, A: torch.Tensor) -> torch.Tensor:
+    """torch 2.11's BATCHED CPU LU (inverse / logdet) is broken in this image when it runs on more than
+    one thread and D > 128 (oneMKL "Parameter 6 was incorrect on entry to SLASWP", corrupt pivots or a
+    hang; profiles/r02_torch_cpu_batched_lu_bug.txt).  The unbatched call is sound, so larger matrices
+    go through it one by one -- the same arithmetic per matrix."""
+    if A.shape[0] > 1 and A.shape[-1] > 128 and torch.get_num_threads() > 1:
+        return torch.stack([fn(a) for a in A])
+    return fn(A)
+
+
+
 def glad_unrolled(S: torch.Tensor, P, L: int = 15, init_diag: int = 0,
                   lambda_init: float = 1.0, trace: Optional[dict] = None) -> torch.Tensor:
     """glad.py:74-150.  S: [B,D,D].  Returns theta_pred [B,D,D] (autograd-connected)."""
@@ -141,7 +152,7 @@ def glad_unrolled(S: torch.Tensor, P, L: int = 15, init_diag: int = 0,
     if init_diag == 1:
         theta = torch.diag_embed(1.0 / (torch.diagonal(S, dim1=-2, dim2=-1) + t0))
     else:
-        theta = torch.linalg.inv(S + t0 * eye)
+        theta = _per_matrix(torch.linalg.inv, S + t0 * eye)
     lam = lambda_net(P, lambda_init, 0.0)
     lams, norms = [lam.detach().clone()], []
     for _ in range(L):
@@ -164,7 +175,7 @@ def glasso_loss(theta: torch.Tensor, S: torch.Tensor,
                 struct_theta: Optional[torch.Tensor] = None) -> torch.Tensor:
     """main.py:289-335: sum_b(-logdet(theta_b) + tr(S_b theta_b)) / B  (+ log-cosh prior)."""
     B, D, _ = S.shape
-    t1 = -torch.logdet(theta)
+    t1 = -_per_matrix(torch.logdet, theta)
     t2 = torch.einsum("bij,bji->b", S, theta)
     loss = torch.sum(t1 + t2) / B
     if struct_theta is not None:
@@ -463,7 +474,7 @@ def fit_missing(X, seed, epochs, lr, k_fold, L=15):
     for _ in range(epochs):
         opt.zero_grad()
         theta = glad_unrolled(S_K, P, L=L)
-        loss = torch.sum(-torch.logdet(theta) + torch.einsum("ij,bji->b", S[0], theta)) / S.shape[0]
+        loss = torch.sum(-_per_matrix(torch.logdet, theta) + torch.einsum("ij,bji->b", S[0], theta)) / S.shape[0]
         loss.backward()
         opt.step()
     return consensus_min(theta.detach())[0].numpy()

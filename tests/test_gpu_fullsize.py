@@ -42,8 +42,8 @@ def _model_from(P):
     return model
 
 
-def _low_threshold_params(seed, bias=-3.5):
-    """rho ~ 0.03: theta keeps a non-trivial off-diagonal support (as after long training)."""
+def _low_threshold_params(seed, bias=-6.0):
+    """rho ~ 0.0025: theta keeps a non-trivial off-diagonal support (as after long training)."""
     P = O.init_params(seed)
     with torch.no_grad():
         P["rho_l1.4.bias"].fill_(bias)
@@ -145,7 +145,7 @@ def test_shards_reproduce_the_whole_batch(D, small_d_max):
         S = torch.tensor(O.covariance(X), dtype=torch.float32).cuda()
         G = torch.tensor(rng.standard_normal((7, D, D)), dtype=torch.float32).cuda()
         G = (G + G.transpose(1, 2)).contiguous()
-        P_ = _low_threshold_params(5, bias=-2.5)
+        P_ = _low_threshold_params(5)
         flat = torch.cat([P_[k].detach().reshape(-1) for k in O.PARAM_KEYS]).cuda()
         dims_fn = lambda B, Bt: ops.make_dims(B, D, L, H, 0, Bt)
         large = D > lib.uglad_small_d_max()
