@@ -208,7 +208,8 @@ def make_mode_cases(ref_main, prepare_data):
     pruned = _quiet(prepare_data.process_table, pd.DataFrame(Z.copy()), NORM="min_max", COND_NUM=200.0, eigval_th=1e-3, VERBOSE=False)
     out["table/collinear_kept"] = np.array(list(pruned.columns), dtype=np.int64)
     out["table/collinear_out"] = np.array(pruned)
-    np.savez_compressed(os.path.join(HERE, "modes.npz"), **out)
+    os.makedirs(os.path.join(HERE, "modes"), exist_ok=True)
+    np.savez_compressed(os.path.join(HERE, "modes", "modes.npz"), **out)
     print("modes: direct(struct prior) / cv / missing / multitask precision_, metrics, process_table;",
           "kept columns under COND_NUM=200:", out["table/collinear_kept"].tolist())
 

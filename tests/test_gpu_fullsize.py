@@ -164,13 +164,13 @@ def test_shards_reproduce_the_whole_batch(D, small_d_max):
             wS, VtS = (eig.wS, eig.VtS) if eig is not None else (None, None)
             ops.check(lib.uglad_glad_init_forward(C.byref(dims), Pp(Ss), Pp(flat), Pp(wS), Pp(VtS), Pp(ws), st), "init")
             state.append((Ss, dims, ws, eig))
-        noff = lib.uglad_workspace_offset(C.byref(state[0][1]), b"normf")
+        noff = [lib.uglad_workspace_offset(C.byref(dims), b"normf") for _, dims, _, _ in state]
         for k in range(L):
             for Ss, dims, ws, eig in state:
                 ops.check(lib.uglad_glad_layer_forward(C.byref(dims), k, Pp(Ss), Pp(flat), Pp(ws), None, st), "layer")
-            total = sum(ws[noff + k] for _, _, ws, _ in state)       # what the all-reduce leaves on every rank
-            for _, _, ws, _ in state:
-                ws[noff + k] = total
+            total = sum(ws[o + k] for o, (_, _, ws, _) in zip(noff, state))       # what the all-reduce leaves on every rank
+            for o, (_, _, ws, _) in zip(noff, state):
+                ws[o + k] = total
         gp_sum = torch.zeros_like(gp_all)
         for sl, (Ss, dims, ws, eig) in zip(shards, state):
             off = lib.uglad_workspace_offset(C.byref(dims), b"theta")
@@ -204,6 +204,9 @@ def test_eigensolver_fixup_list_recheck_and_overflow_branches():
             Q, _ = np.linalg.qr(rng.standard_normal((D, D)))
             ev = np.concatenate([1.0 + spread * rng.standard_normal(D - 6), np.array([-3.0, -1.0, 0.2, 2.5, 4.0, 9.0])])
             mats.append((Q * ev) @ Q.T)
+    for D in (8, 10, 11):   # at most 64 column pairs: a cold sweep leaves a short list of LARGE cosines -> re-check
+        A = rng.standard_normal((D, D))
+        mats.append((A + A.T) / 2)
     seen = np.zeros(3)
     ops.tune("eig_timing", 2)
     try:

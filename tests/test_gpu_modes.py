@@ -29,7 +29,7 @@ def edges_match(theta, ref, margin=1e-5):
 
 @pytest.fixture(scope="module")
 def g():
-    return np.load(os.path.join(ROOT, "tests", "golden", "modes.npz"))
+    return np.load(os.path.join(ROOT, "tests", "golden", "modes", "modes.npz"))
 
 
 @pytest.fixture(autouse=True)

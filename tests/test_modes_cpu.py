@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.fixture(scope="module")
 def g():
-    return np.load(os.path.join(ROOT, "tests", "golden", "modes.npz"))
+    return np.load(os.path.join(ROOT, "tests", "golden", "modes", "modes.npz"))
 
 
 def rel(a, b):

@@ -282,7 +282,7 @@ static int condition_large(float* S, int B, int D, float offset, float* scratch,
   double* work64 = reinterpret_cast<double*>(cs + al4(chol_scratch_floats(B, D)));
   double* mu64_dev = work64 + n2;
   int* active_dev = reinterpret_cast<int*>(mu64_dev + B);
-  int* fail64_dev = active_dev + B;
+  int* fail64_dev = active_dev + al4(B);   // al4: what follows holds doubles again
   double* S64 = (X && mean && M > 0) ? reinterpret_cast<double*>(fail64_dev + al4(B)) : nullptr;
   std::vector<float> tr(B), mu(B);
   std::vector<int> fail(B);

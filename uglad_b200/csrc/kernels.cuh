@@ -30,9 +30,11 @@ struct EigArgs {
   int use_mma = 1;               // warm-start product / Rayleigh quotients via mma.sync (3xTF32)
   int timing = 0;                // developer knob: info[1..3] <- phase cycle counts
   unsigned long long* work = nullptr;   // profiling: {column-pair dot products, applied rotations} accumulated over CTAs
-  float tol = 1e-6f;   // cosine threshold.  2e-6 is 4 % faster and keeps theta within 1.8e-5 of the reference, but on the
-                       // trained low-threshold golden it left an entry of 1.2e-5 where the reference has an exact zero
-                       // (edge criterion: 1e-5); 1e-6 leaves 2e-6 there (scripts/gpu_edge_margin.py)
+  float tol = 5e-7f;   // cosine threshold.  Round 1 ran 1e-6 (2e-6 had left an entry of 1.2e-5 on the trained low-threshold
+                       // golden where the reference has an exact zero; edge criterion: 1e-5).  At BASELINE's full size
+                       // (256 x D=100, 2.56 M entries) the warm-started solves at 1e-6 still left 2 such entries (1.22e-5);
+                       // 5e-7 halves the off-diagonal error (2.6e-5 -> 1.3e-5 max abs against the FP32 reference), leaves
+                       // none, and costs < 4 % of the forward; 3e-7 costs 20 % (profiles/r02_edge_margin_fullsize.txt)
 };
 int launch_eig_small(const EigArgs& a, int B, cudaStream_t st);
 int eig_small_tune(const char* key, int value);
