@@ -524,9 +524,14 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     group = None
+    numa = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
+        # N processes stream their samples from one host at once: keep each one's pinned staging memory and
+        # threads on the NUMA node of its GPU
+        from uglad_b200.utils import prepare_data as _pd
+        numa = _pd.bind_host_to_device_numa(dev)
 
     peaks = {}
     try:
@@ -575,7 +580,7 @@ def main():
             "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl, "baseline_config_index": spec["config_index"], "graphs_per_gpu": B,
                        "graphs_total": r["B_total"], "D": D, "M": r["M"], "L": L_LAYERS, "H": 3,
-                       "parallelism": f"graph-sharded x{world}", "l2_policy": "working set per step exceeds L2 "
+                       "parallelism": f"graph-sharded x{world}", "host_numa_node": numa, "l2_policy": "working set per step exceeds L2 "
                        "(saved theta / theta_k1 / eigenvectors of 15 layers: %.0f MB)" % (B * D * D * 4 * 3 * L_LAYERS / 1e6)},
             "clocks": r["clocks"],
             "e2e": {"value": r["e2e_value"], "unit": UNIT, "ms_per_step": r["e2e_ms_per_step"],

@@ -120,6 +120,30 @@ int uglad_glad_layer_forward(const uglad_dims* d, int k, const float* S, const f
 int uglad_glad_forward(const uglad_dims* d, const float* S, const float* params,
                        const float* wS, const float* VtS, float* ws, const float* warm_ws,
                        void* stream);
+/* The same on ONE shard of a graph-sharded batch (B_total > B), still in one call.  The graphs of a
+ * multitask / consensus batch are coupled only by the batch mean of ||Z - X||_F^2 after every layer
+ * (glad.py:147).  Every rank owns an exchange buffer of uglad_peer_slots_bytes(L) bytes that all ranks
+ * of the box have mapped (uglad_peer_alloc / uglad_peer_open: CUDA IPC over NVLink peer access); the
+ * lambda kernel of layer k + 1 stores its local sum into every rank's buffer and adds up what the
+ * other ranks stored into its own -- in rank order, so every rank computes the same lambda bit for
+ * bit.  `tag` must be the same on all ranks and different from the previous call's (a call counter).
+ * Between two calls the ranks must have met (the gradient all-reduce of the epoch, or a barrier).    */
+#define UGLAD_MAX_PEERS 8
+typedef struct uglad_peers {
+  int world;                      /* ranks sharing the batch (<= UGLAD_MAX_PEERS, one box)           */
+  int rank;                       /* this process                                                     */
+  unsigned tag;                   /* call counter, identical on all ranks                             */
+  void* slots[UGLAD_MAX_PEERS];   /* device pointers (valid in THIS process) to every rank's buffer  */
+} uglad_peers;
+size_t uglad_peer_slots_bytes(int L);
+int uglad_glad_forward_sharded(const uglad_dims* d, const float* S, const float* params, const float* wS,
+                               const float* VtS, float* ws, const float* warm_ws, const uglad_peers* peers,
+                               void* stream);
+/* exchange-buffer plumbing: cudaMalloc + zero + cudaIpcGetMemHandle (64 bytes, to be sent to the
+ * other ranks) / cudaIpcOpenMemHandle of a peer's handle / release (opened = 1 for peer mappings).  */
+int uglad_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+int uglad_peer_open(const unsigned char* handle64, void** ptr);
+int uglad_peer_close(void* ptr, int opened);
 /* backward of the above: grad_theta[B][D][D] -> grad_params[uglad_param_count(H)] (local
  * contribution; the caller all-reduces it over processes).                               */
 int uglad_glad_backward(const uglad_dims* d, const float* S, const float* params,

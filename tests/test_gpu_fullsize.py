@@ -260,3 +260,56 @@ def test_covariance_repair_decision_near_the_threshold(small_d_max, min_eig, rep
         assert rel(S, want) < 1e-5, (rel(S, want), np.abs(S[0] - raw).max())
     finally:
         ops.tune("small_d_max", 166)
+
+
+@pytest.mark.parametrize("D,small_d_max", [(20, 166), (20, 0), (100, 166)], ids=["eigensolver", "large-path", "d100"])
+def test_peer_exchange_forward_reproduces_the_whole_batch(D, small_d_max):
+    """uglad_glad_forward_sharded: two shards of one batch as two "ranks" on two streams of this GPU,
+    their exchange buffers mapped into each other (here: plain device pointers of one process; across
+    processes the same pointers come from CUDA IPC).  The lambda kernels exchange the per-layer Frobenius
+    sums through those buffers; the shards must reproduce uglad_glad_forward on the whole batch, and two
+    consecutive calls (alternating slot parity, new tags) must both be right."""
+    from uglad_b200 import _lib, ops
+    lib = _lib.load()
+    ops.tune("small_d_max", small_d_max)
+    try:
+        L, H = 6, 3
+        rng = np.random.default_rng(D + 1)
+        X = rng.random((5, 3 * D, D))
+        S = torch.tensor(O.covariance(X), dtype=torch.float32).cuda()
+        P_ = _low_threshold_params(6)
+        flat = torch.cat([P_[k].detach().reshape(-1) for k in O.PARAM_KEYS]).cuda()
+        large = D > lib.uglad_small_d_max()
+        G = torch.zeros(5, D, D, device="cuda")
+        eig_all = None if large else ops.ConditionedCovariance(S, repair=False)
+        theta_all, _ = _run_whole(lib, lambda B, Bt: ops.make_dims(B, D, L, H, 0, Bt), S, flat, eig_all, G)
+        Pp = lambda t: C.c_void_p(0 if t is None else t.data_ptr())
+        shards = [slice(0, 3), slice(3, 5)]
+        streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        slots = [torch.zeros(lib.uglad_peer_slots_bytes(L) // 8, dtype=torch.int64, device="cuda") for _ in shards]
+        state = []
+        for sl in shards:
+            Ss = S[sl].contiguous()
+            dims = ops.make_dims(Ss.shape[0], D, L, H, 0, 5)
+            ws = torch.empty(lib.uglad_workspace_floats(C.byref(dims)), device="cuda")
+            eig = None if large else ops.ConditionedCovariance(Ss, repair=False)
+            state.append((Ss, dims, ws, eig))
+        torch.cuda.synchronize()
+        for tag in (7, 8):
+            for r, ((Ss, dims, ws, eig), stream) in enumerate(zip(state, streams)):
+                peers = _lib.UgladPeers()
+                peers.world, peers.rank, peers.tag = 2, r, tag
+                for j, t in enumerate(slots):
+                    peers.slots[j] = t.data_ptr()
+                wS, VtS = (eig.wS, eig.VtS) if eig is not None else (None, None)
+                ops.check(lib.uglad_glad_forward_sharded(C.byref(dims), Pp(Ss), Pp(flat), Pp(wS), Pp(VtS), Pp(ws), None,
+                                                         C.byref(peers), C.c_void_p(stream.cuda_stream)), "forward_sharded")
+            torch.cuda.synchronize()
+            for sl, (Ss, dims, ws, eig) in zip(shards, state):
+                off = lib.uglad_workspace_offset(C.byref(dims), b"theta")
+                n = Ss.shape[0]
+                theta = ws[off:off + n * D * D].view(n, D, D)
+                assert rel(theta.cpu().numpy(), theta_all[sl].cpu().numpy()) < 2e-6, tag
+                assert edges_match(theta.cpu().numpy(), theta_all[sl].cpu().numpy())
+    finally:
+        ops.tune("small_d_max", 166)

@@ -18,6 +18,10 @@ class UgladDims(C.Structure):
                 ("lambda_init", C.c_float)]
 
 
+class UgladPeers(C.Structure):
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("tag", C.c_uint), ("slots", C.c_void_p * 8)]
+
+
 # name -> (restype, argtypes); every symbol include/uglad_b200.h declares
 _P, _I, _F, _Z = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 _DP = C.POINTER(UgladDims)
@@ -42,6 +46,11 @@ SIGNATURES = {
     "uglad_glad_layer_forward": (_I, [_DP, _I, _P, _P, _P, _P, _P]),
     "uglad_glad_forward": (_I, [_DP, _P, _P, _P, _P, _P, _P, _P]),
     "uglad_glad_backward": (_I, [_DP, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "uglad_peer_slots_bytes": (_Z, [_I]),
+    "uglad_glad_forward_sharded": (_I, [_DP, _P, _P, _P, _P, _P, _P, C.POINTER(UgladPeers), _P]),
+    "uglad_peer_alloc": (_I, [_Z, C.POINTER(C.c_void_p), C.c_char_p]),
+    "uglad_peer_open": (_I, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "uglad_peer_close": (_I, [_P, _I]),
     "uglad_loss_scratch_floats": (_Z, [_I, _I]),
     "uglad_glasso_loss": (_I, [_P, _P, _I, _I, _I, _F, _P, _P, _P, _P]),
     "uglad_glasso_loss_prior": (_I, [_P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P]),

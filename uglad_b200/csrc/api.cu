@@ -423,8 +423,14 @@ int uglad_glad_init_forward(const uglad_dims* d, const float* S, const float* pa
   return spectral_recon(VtS, ws + w.f0, ws + w.theta, d->B, d->D, 1.f, nullptr, 0, st);
 }
 
+static int layer_forward_impl(const uglad_dims* d, int k, const float* S, const float* params, float* ws,
+                              const float* warm_ws, void* stream, const PeerSlots* peers);
 int uglad_glad_layer_forward(const uglad_dims* d, int k, const float* S, const float* params,
                              float* ws, const float* warm_ws, void* stream) {
+  return layer_forward_impl(d, k, S, params, ws, warm_ws, stream, nullptr);
+}
+static int layer_forward_impl(const uglad_dims* d, int k, const float* S, const float* params, float* ws,
+                              const float* warm_ws, void* stream, const PeerSlots* peers) {
   if (check_dims(d)) return 1;
   if (k < 0 || k >= d->L) { set_error("glad_layer_forward: k=%d outside [0,%d)", k, d->L); return 1; }
   cudaStream_t st = (cudaStream_t)stream;
@@ -436,7 +442,7 @@ int uglad_glad_layer_forward(const uglad_dims* d, int k, const float* S, const f
   float* Vk = ws + w.Vt + (size_t)k * w.n2;
   float* fk = ws + w.f + (size_t)k * w.n1;
   if (launch_lambda_step(k, params, d->H, d->lambda_init, d->B_total, ws + w.normf, ws + w.lam,
-                         ws + w.lamfeat, st)) return 1;
+                         ws + w.lamfeat, st, peers, d->L)) return 1;
   if (w.large) {
     if (ns_theta_update_forward(S, (long long)D * D, theta_prev, ws + w.lam + k, B, D, Xk, ws + w.ns_scratch, st))
       return 1;
@@ -478,6 +484,53 @@ int uglad_glad_forward(const uglad_dims* d, const float* S, const float* params,
   if (uglad_glad_init_forward(d, S, params, wS, VtS, ws, stream)) return 1;
   for (int k = 0; k < d->L; ++k)
     if (uglad_glad_layer_forward(d, k, S, params, ws, warm_ws, stream)) return 1;
+  return 0;
+}
+
+// glad.py:74-150 on ONE shard of a graph-sharded batch, in one call: the per-layer Frobenius sums are
+// exchanged between the ranks by the lambda kernels themselves through peer-mapped buffers (see
+// lambda_step_kernel), so no host code or collective runs between the layers.
+int uglad_glad_forward_sharded(const uglad_dims* d, const float* S, const float* params, const float* wS,
+                               const float* VtS, float* ws, const float* warm_ws, const uglad_peers* peers,
+                               void* stream) {
+  if (check_dims(d)) return 1;
+  if (!peers || peers->world < 1 || peers->world > UGLAD_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world) {
+    set_error("glad_forward_sharded: bad peer description (world must lie in [1, %d])", UGLAD_MAX_PEERS);
+    return 1;
+  }
+  PeerSlots ps;
+  ps.world = peers->world; ps.rank = peers->rank; ps.tag = peers->tag;
+  for (int r = 0; r < peers->world; ++r) {
+    if (!peers->slots[r]) { set_error("glad_forward_sharded: slots[%d] is NULL", r); return 1; }
+    ps.slots[r] = reinterpret_cast<unsigned long long*>(peers->slots[r]);
+  }
+  if (uglad_glad_init_forward(d, S, params, wS, VtS, ws, stream)) return 1;
+  for (int k = 0; k < d->L; ++k)
+    if (layer_forward_impl(d, k, S, params, ws, warm_ws, stream, &ps)) return 1;
+  return 0;
+}
+size_t uglad_peer_slots_bytes(int L) { return (size_t)2 * (L > 0 ? L : 1) * UGLAD_MAX_PEERS * sizeof(unsigned long long); }
+int uglad_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64) {
+  if (!ptr || !handle64 || bytes == 0) { set_error("peer_alloc: bad arguments"); return 1; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  UGLAD_CUDA(cudaMalloc(ptr, bytes));
+  UGLAD_CUDA(cudaMemset(*ptr, 0, bytes));
+  cudaIpcMemHandle_t h;
+  UGLAD_CUDA(cudaIpcGetMemHandle(&h, *ptr));
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+int uglad_peer_open(const unsigned char* handle64, void** ptr) {
+  if (!ptr || !handle64) { set_error("peer_open: bad arguments"); return 1; }
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  UGLAD_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+int uglad_peer_close(void* ptr, int opened) {
+  if (!ptr) return 0;
+  if (opened) { UGLAD_CUDA(cudaIpcCloseMemHandle(ptr)); }
+  else { UGLAD_CUDA(cudaFree(ptr)); }
   return 0;
 }
 

@@ -25,8 +25,16 @@ __device__ __forceinline__ void load_params_smem(float* sw, const float* params,
 // ------------------------------------------------------------------------------------------
 // lambda_k = lambda_f([normF_{k-1} / B_total, lambda_{k-1}])   (glad.py:135,146-150,
 // glad_params.py:79-91).  One warp.  Stores the input features for the backward.
+//
+// Graph-sharded execution (peers.world > 1): the batch mean runs over the graphs of ALL ranks.  Each
+// rank's exchange buffer holds slots[parity][layer][rank] of 64-bit words {tag : 32 | float bits : 32};
+// this kernel publishes the local sum of layer k - 1 into the slot [k - 1][rank] of EVERY rank's buffer
+// (peer-mapped memory: plain stores over NVLink), then waits until the slots of all ranks in its own
+// buffer carry the current tag, adds them in rank order (every rank forms the same sum, bit for bit)
+// and leaves the global sum in normf[k - 1].  No host round trip, no collective: the whole sharded
+// forward is one stream of kernels.  A lost peer faults after ~10 s instead of hanging the GPU.
 __global__ void lambda_step_kernel(int k, const float* params, int H, float lambda_init,
-                                   int B_total, const float* normf, float* lam, float* lamfeat) {
+                                   int B_total, float* normf, float* lam, float* lamfeat, PeerSlots peers, int L) {
   if (threadIdx.x != 0) return;
   const ParamLayout pl = param_layout(H);
   float x0, x1;
@@ -34,7 +42,34 @@ __global__ void lambda_step_kernel(int k, const float* params, int H, float lamb
     x0 = lambda_init;
     x1 = 0.f;
   } else {
-    x0 = normf[k - 1] / (float)B_total;
+    float total = normf[k - 1];
+    if (peers.world > 1) {
+      const size_t slot = ((size_t)(peers.tag & 1u) * L + (k - 1)) * UGLAD_MAX_PEERS;
+      const unsigned long long word = ((unsigned long long)peers.tag << 32) | (unsigned long long)__float_as_uint(total);
+      for (int r = 0; r < peers.world; ++r) {
+        volatile unsigned long long* dst = peers.slots[r] + slot + peers.rank;
+        *dst = word;
+      }
+      __threadfence_system();
+      const volatile unsigned long long* mine = peers.slots[peers.rank] + slot;
+      total = 0.f;
+      long long t0 = 0;
+      for (int r = 0; r < peers.world; ++r) {
+        unsigned long long w;
+        for (int spin = 0;; ++spin) {
+          w = mine[r];
+          if ((unsigned)(w >> 32) == peers.tag) break;
+          if ((spin & 1023) == 1023) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 20000000000LL) asm volatile("trap;");
+          }
+        }
+        total += __uint_as_float((unsigned)(w & 0xffffffffull));
+      }
+      normf[k - 1] = total;   // what the all-reduce used to leave here
+    }
+    x0 = total / (float)B_total;
     x1 = lam[k - 1];
   }
   float o = params[pl.lb2];
@@ -47,8 +82,9 @@ __global__ void lambda_step_kernel(int k, const float* params, int H, float lamb
   lamfeat[2 * k + 1] = x1;
 }
 int launch_lambda_step(int k, const float* params, int H, float lambda_init, int B_total,
-                       const float* normf, float* lam, float* lamfeat, cudaStream_t st) {
-  lambda_step_kernel<<<1, 32, 0, st>>>(k, params, H, lambda_init, B_total, normf, lam, lamfeat);
+                       float* normf, float* lam, float* lamfeat, cudaStream_t st, const PeerSlots* peers, int L) {
+  PeerSlots none;
+  lambda_step_kernel<<<1, 32, 0, st>>>(k, params, H, lambda_init, B_total, normf, lam, lamfeat, peers ? *peers : none, L);
   UGLAD_CHECK_LAUNCH("lambda_step_kernel");
   return 0;
 }

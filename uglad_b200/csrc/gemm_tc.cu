@@ -40,6 +40,7 @@
 // allocation, descriptor prefetch) runs under the tail of the previous kernel, griddepcontrol.wait
 // guards the first access to its results.
 #include <cuda.h>
+#include <string.h>
 #include <mutex>
 #include <unordered_map>
 #include "kernels.cuh"
@@ -745,6 +746,335 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 
 
 // ---------------------------------------------------------------------------------------------
+// Persistent CHAIN of dependent products (the Newton-Schulz iterations of the large-D path).
+//
+// One launch runs a whole list of stages; a stage is one product or two independent products of
+// the same D x D x D shape (plus, optionally, the in-place antisymmetrisation W <- W - W^T of one
+// buffer, done by the epilogue warps before their tiles).  Consecutive stages depend on each other
+// through whole matrices, so they are separated by a grid-wide barrier: every CTA (one per SM, all
+// co-resident) publishes the end of its tiles of stage s on a global counter, and the TMA producer
+// of every CTA waits for that counter before its first load of stage s + 1.  Everything else of
+// the pipeline -- the shared-memory slab ring, the split warps, the two TMEM accumulator stages --
+// runs straight through the stage boundaries.
+//
+// Why: as separate launches every product of the chain is ONE tile per CTA, and the launch, the
+// dependency wait, the first TMA round trip, the epilogue and the teardown of each of the ~50
+// launches per layer are all exposed (at D = 1000 the MMA main loop is ~9 us of a ~26-32 us launch;
+// at 32 x D = 200 ~2 us of ~20 us).  The chain pays launch and teardown once and a ~2 us barrier
+// per stage.
+//
+// Operands are plain FP32 [batch][D][ld] buffers (raw mode: lo = x - trunc(x) formed in shared
+// memory).  A buffer has ONE tensor map per box height (128 rows for the A operand and for the
+// C stores -- the store box is the same 32 x 128 box -- and BN rows for the B operand), so a stage
+// only names buffer indices and the whole description travels as a kernel parameter.
+namespace tc {
+constexpr int CH_MAX_BUF = 12, CH_MAX_STAGE = 40;
+}
+struct ChainProb {
+  int a, b, c, e1;            // buffer indices: C = alpha A B^T + beta E1 + diag I   (e1 < 0: no addend)
+  float alpha, beta, diag;
+  const float* alpha_dev;     // optional per-graph factor of alpha
+};
+struct ChainStage {
+  int nprob;                  // 1 or 2 independent products
+  int antisym;                // >= 0: buffer to antisymmetrise in place (W <- W - W^T) before this stage's tiles
+  ChainProb p[2];
+};
+struct ChainBuf {
+  float* ptr;
+  long long stride;           // floats between graphs
+  int ld;
+  int tma;                    // 1: rows are 16-byte multiples -> has tensor maps (operand / TMA-stored output)
+};
+struct ChainParams {
+  CUtensorMap mapA[tc::CH_MAX_BUF];   // box 32 x 128 (A operand, C store)
+  CUtensorMap mapB[tc::CH_MAX_BUF];   // box 32 x BN  (B operand)
+  ChainBuf buf[tc::CH_MAX_BUF];
+  ChainStage st[tc::CH_MAX_STAGE];
+  int nstages, M, N, K, batch, tiles_m, tiles_n;
+  unsigned* barrier;                  // zeroed before the launch
+  long long* dbg;                     // developer timeline [stage][CTA][8] of %globaltimer stamps (null = off)
+};
+
+namespace tc {
+__device__ __forceinline__ long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return (long long)t;
+}
+// wait until `target` CTAs-times-stages have arrived; faults (never hangs) if an arrival is lost
+__device__ __forceinline__ void grid_wait(const unsigned* bar, unsigned target) {
+  unsigned v = 0;
+  long long t0 = 0;
+  for (int spin = 0;; ++spin) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+    if (v >= target) break;
+    if ((spin & 255) == 255) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000LL) asm volatile("trap;");
+    }
+  }
+  __threadfence();                                             // L1 of this SM holds nothing older than the arrivals
+  asm volatile("fence.proxy.async.global;" ::: "memory");      // ... and neither do the TMA (async proxy) reads that follow
+}
+__device__ __forceinline__ void grid_arrive(unsigned* bar) {
+  asm volatile("fence.proxy.async.global;" ::: "memory");      // completed TMA stores -> generic proxy
+  __threadfence();
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+}
+}  // namespace tc
+
+template <int BN>
+__global__ void __launch_bounds__(tc::THREADS_RAW, 1) tc_chain_kernel(const __grid_constant__ ChainParams P) {
+  using C = tc::Cfg<BN>;
+  static_assert(BN % 32 == 0, "the chain stores C through the 32-column TMA box only");
+  constexpr int EPI_WARPS = tc::EPI_WARPS_RAW;
+  constexpr int ROLE_THREADS = 64 + 32 * EPI_WARPS;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = tc::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  const uint32_t bar0 = base + C::STAGES * C::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * C::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * C::STAGES + 2 + a); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * C::STAGES + 4);
+  auto split_bar = [&](int s) { return bar0 + 8u * (2 * C::STAGES + 5 + s); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) { tc::mbar_init(full_bar(s), 1); tc::mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { tc::mbar_init(tfull_bar(a), 1); tc::mbar_init(tempty_bar(a), EPI_WARPS); }
+    for (int s = 0; s < C::STAGES; ++s) tc::mbar_init(split_bar(s), tc::SPLIT_WARPS / 2);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32((const void*)tmem_slot)), "r"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  const int tiles_per_prob = P.tiles_m * P.tiles_n;
+  const int num_kb = (P.K + tc::BK - 1) / tc::BK;
+  const int G = (int)gridDim.x;
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int s = 0; s < P.nstages; ++s) {
+        long long* dg = P.dbg ? P.dbg + ((size_t)s * G + blockIdx.x) * 8 : nullptr;
+        if (dg) dg[0] = tc::gtime();
+        if (s > 0) tc::grid_wait(P.barrier, (unsigned)s * (unsigned)G);   // every CTA is done with stage s - 1
+        if (dg) dg[1] = tc::gtime();
+        const ChainStage& S = P.st[s];
+        const int tiles_per_batch = tiles_per_prob * S.nprob;
+        const int total_tiles = tiles_per_batch * P.batch;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += G) {
+          const int b = tile / tiles_per_batch, r0 = tile - b * tiles_per_batch;
+          const int prob = r0 / tiles_per_prob, r = r0 - prob * tiles_per_prob;
+          const int tm = r / P.tiles_n, tn = r - tm * P.tiles_n;
+          const CUtensorMap* mA = &P.mapA[S.p[prob].a];
+          const CUtensorMap* mB = &P.mapB[S.p[prob].b];
+          for (int kb = 0; kb < num_kb; ++kb) {
+            tc::mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t sa = base + stage * C::STAGE_BYTES;
+            tc::mbar_arrive_expect_tx(full_bar(stage), C::RAW_TX_BYTES);
+            tc::tma_load_3d(sa, mA, full_bar(stage), kb * tc::BK, tm * tc::BM, b);
+            tc::tma_load_3d(sa + 2 * tc::A_BYTES, mB, full_bar(stage), kb * tc::BK, tn * BN, b);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (tc::elect_one()) {
+      const uint64_t d0 = tc::umma_desc(base);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int s = 0; s < P.nstages; ++s) {
+        const int total_tiles = tiles_per_prob * P.st[s].nprob * P.batch;
+        long long* dg = P.dbg ? P.dbg + ((size_t)s * G + blockIdx.x) * 8 : nullptr;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += G) {
+          tc::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+          tc::tc_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * C::ACC_STRIDE;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            tc::mbar_wait(split_bar(stage), phase);
+            tc::tc_fence_after();
+            if (dg && kb == 0 && tile == (int)blockIdx.x) dg[2] = tc::gtime();
+            const int krem = P.K - kb * tc::BK;
+            const int ngran = krem >= tc::BK ? 4 : (krem + 7) >> 3;
+            switch (stage) {
+              case 0: tc_issue_slab<BN, 0>(d0, tmem_d, ngran, kb == 0); break;
+              case 1: tc_issue_slab<BN, C::STAGE_BYTES>(d0, tmem_d, ngran, kb == 0); break;
+              case 2: tc_issue_slab<BN, 2 * C::STAGE_BYTES>(d0, tmem_d, ngran, kb == 0); break;
+              default: tc_issue_slab<BN, (C::STAGES - 1) * C::STAGE_BYTES>(d0, tmem_d, ngran, kb == 0); break;
+            }
+            tc::umma_commit(empty_bar(stage));
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+          }
+          tc::umma_commit(tfull_bar(acc));
+          if (dg) dg[3] = tc::gtime();
+          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 2 + EPI_WARPS) {
+    // split warps: the slabs of all stages form one sequence through the ring
+    constexpr int NT = 32 * tc::SPLIT_WARPS / 2;
+    const int t = (threadIdx.x - ROLE_THREADS) % NT, grp = (threadIdx.x - ROLE_THREADS) / NT;
+    constexpr int A_CH = tc::A_BYTES / 16, B_CH = C::B_BYTES / 16;
+    long long nslab = 0;
+    for (int s = 0; s < P.nstages; ++s) {
+      const int total_tiles = tiles_per_prob * P.st[s].nprob * P.batch;
+      const long long my_tiles = total_tiles > (int)blockIdx.x ? (total_tiles - 1 - (int)blockIdx.x) / G + 1 : 0;
+      nslab += my_tiles * num_kb;
+    }
+    for (long long i = 0; i < nslab; ++i) {
+      const int stage = (int)(i % C::STAGES);
+      const uint32_t phase = (uint32_t)((i / C::STAGES) & 1);
+      tc::mbar_wait(full_bar(stage), phase);     // every group waits for every slab in order (see tc_gemm_kernel)
+      if ((int)(i & 1) != grp) continue;
+      uint8_t* sa = smem + stage * C::STAGE_BYTES;
+      const float4* a_hi = reinterpret_cast<const float4*>(sa);
+      float4* a_lo = reinterpret_cast<float4*>(sa + tc::A_BYTES);
+      const float4* b_hi = reinterpret_cast<const float4*>(sa + 2 * tc::A_BYTES);
+      float4* b_lo = reinterpret_cast<float4*>(sa + 2 * tc::A_BYTES + C::B_BYTES);
+      constexpr int BATCH = 8;
+#pragma unroll
+      for (int j0 = 0; j0 < A_CH / NT; j0 += BATCH) {
+        float4 x[BATCH];
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) x[j] = a_hi[t + (j0 + j) * NT];
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) a_lo[t + (j0 + j) * NT] = tc::lo4(x[j]);
+      }
+      constexpr int B_IT = (B_CH + NT - 1) / NT;
+#pragma unroll
+      for (int j0 = 0; j0 < B_IT; j0 += BATCH) {
+        float4 x[BATCH];
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j)
+          if (j0 + j < B_IT && (B_CH % NT == 0 || t + (j0 + j) * NT < B_CH)) x[j] = b_hi[t + (j0 + j) * NT];
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j)
+          if (j0 + j < B_IT && (B_CH % NT == 0 || t + (j0 + j) * NT < B_CH)) b_lo[t + (j0 + j) * NT] = tc::lo4(x[j]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(split_bar(stage));
+    }
+  } else {
+    // epilogue warps (128 threads): per stage [optional antisymmetrisation], the tiles, then the arrival
+    const int q = warp & 3;
+    const bool leader = warp == 2 && lane == 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    int cbuf = 0;
+    uint8_t* cst = smem + C::STAGES * C::STAGE_BYTES + 1024;
+    const uint32_t cst_s = base + C::STAGES * C::STAGE_BYTES + 1024;
+    TcParams tp;
+    tp.M = P.M; tp.N = P.N;
+    for (int s = 0; s < P.nstages; ++s) {
+      const ChainStage& S = P.st[s];
+      if (S.antisym >= 0) {
+        // W <- W - W^T in place, mirrored 32 x 32 tile pairs spread over the CTAs.  Its input was written by
+        // stage s - 1 (other CTAs), its result is read by stage s + 1: both sides are covered by the barriers.
+        if (leader) {
+          tc::tma_store_wait_all();                       // the staging area doubles as the transpose buffer
+          if (s > 0) tc::grid_wait(P.barrier, (unsigned)s * (unsigned)G);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const ChainBuf W = P.buf[S.antisym];
+        float (*ta)[33] = reinterpret_cast<float (*)[33]>(cst);
+        float (*tb)[33] = reinterpret_cast<float (*)[33]>(cst + 32 * 33 * 4);
+        const int nt = (P.M + 31) / 32, ty = warp - 2, tx = lane;
+        const int npair = nt * nt * P.batch;
+        for (int pr = blockIdx.x; pr < npair; pr += G) {
+          const int bb = pr / (nt * nt), rr = pr - bb * nt * nt;
+          const int bxi = rr / nt, byi = rr - bxi * nt;
+          if (bxi > byi) continue;                        // uniform over the CTA
+          const int bx = bxi * 32, by = byi * 32;
+          float* Wb = W.ptr + (size_t)bb * W.stride;
+          for (int r = ty; r < 32; r += 4) {
+            ta[r][tx] = (bx + r < P.M && by + tx < P.M) ? Wb[(size_t)(bx + r) * W.ld + by + tx] : 0.f;
+            tb[r][tx] = (by + r < P.M && bx + tx < P.M) ? Wb[(size_t)(by + r) * W.ld + bx + tx] : 0.f;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int r = ty; r < 32; r += 4) {
+            if (bx + r < P.M && by + tx < P.M) Wb[(size_t)(bx + r) * W.ld + by + tx] = ta[r][tx] - tb[tx][r];
+            if (bxi != byi && by + r < P.M && bx + tx < P.M) Wb[(size_t)(by + r) * W.ld + bx + tx] = tb[r][tx] - ta[tx][r];
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the area goes back to the TMA stores
+      }
+      const int tiles_per_batch = tiles_per_prob * S.nprob;
+      const int total_tiles = tiles_per_batch * P.batch;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += G) {
+        const int b = tile / tiles_per_batch, r0 = tile - b * tiles_per_batch;
+        const int prob = r0 / tiles_per_prob, r = r0 - prob * tiles_per_prob;
+        const int tm = r / P.tiles_n, tn = r - tm * P.tiles_n;
+        const ChainProb& cp = S.p[prob];
+        const ChainBuf cb = P.buf[cp.c];
+        TcEpi ep;
+        ep.alpha = cp.alpha; ep.beta = cp.beta; ep.diag = cp.diag; ep.alpha_dev = cp.alpha_dev;
+        ep.E1_lo = nullptr; ep.C_lo = nullptr;
+        if (cp.e1 >= 0) { const ChainBuf eb = P.buf[cp.e1]; ep.E1_hi = eb.ptr; ep.sE1 = eb.stride; ep.lde1 = eb.ld; }
+        else { ep.E1_hi = nullptr; ep.sE1 = 0; ep.lde1 = 0; }
+        ep.C_hi = cb.ptr; ep.sC = cb.stride; ep.ldc = cb.ld;
+        tc::mbar_wait(tfull_bar(acc), acc_phase);
+        tc::tc_fence_after();
+        if (P.dbg && leader) P.dbg[((size_t)s * G + blockIdx.x) * 8 + 4] = tc::gtime();   // accumulator of the (last) tile visible
+        if (cb.tma) {
+          tc_epilogue_tile_tma<BN>(tp, ep, &P.mapA[cp.c], &P.mapA[cp.c], tmem_base + acc * C::ACC_STRIDE, tm, tn, b, q, lane,
+                                   cst, cst_s, cbuf, leader);
+        } else {
+          tc_epilogue_tile<BN, EPI_WARPS>(tp, ep, tmem_base + acc * C::ACC_STRIDE, tm, tn, b, q, 0, lane, nullptr, nullptr);
+        }
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(tempty_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+      // end of this CTA's share of stage s: direct stores of all 128 threads and the TMA stores of the leader
+      // are complete and visible before the arrival.  The counter is cumulative (target (s + 1) G), so an
+      // arrival for stage s must never be counted before stage s - 1 is complete EVERYWHERE: a CTA without a
+      // tile in stage s would otherwise run ahead and let the count reach the target while a slow CTA is
+      // still inside stage s - 1.  (A CTA with tiles has passed that barrier already: its loads waited for it.)
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (leader) {
+        long long* dg = P.dbg ? P.dbg + ((size_t)s * G + blockIdx.x) * 8 : nullptr;
+        if (dg) dg[5] = tc::gtime();                      // epilogues issued
+        tc::tma_store_wait_all();
+        if (dg) dg[6] = tc::gtime();                      // stores complete
+        if (s > 0) tc::grid_wait(P.barrier, (unsigned)s * (unsigned)G);
+        tc::grid_arrive(P.barrier);
+        if (dg) dg[7] = tc::gtime();                      // arrived
+      }
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc::tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
 // host side: tensor maps (cached: the operands live in a handful of fixed scratch matrices)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -975,4 +1305,89 @@ int launch_tc_gemm2(const TcGemm& g1, const TcGemm& g2, int batch, cudaStream_t 
                    : (launch_tc_any(g1, nullptr, batch, st) || launch_tc_any(g2, nullptr, batch, st));
 }
 
+
+// ---- host side of the persistent chain ----------------------------------------------------------
+static int g_tc_chain = 1;      // 1 (default): the Newton-Schulz iterations run as one persistent chain launch
+static int g_tc_chain_bn = 0;   // 0 auto / 64 / 128
+int tc_tune_chain(int on) { g_tc_chain = on ? 1 : 0; return 0; }
+int tc_tune_chain_bn(int bn) { g_tc_chain_bn = bn; return 0; }
+bool tc_chain_enabled() { return g_tc_chain != 0 && g_tc_raw != 0; }
+
+template <int BN>
+static int launch_chain_bn(const TcChain& c, cudaStream_t st) {
+  using C = tc::Cfg<BN>;
+  static bool attr_set[MAX_DEV] = {false};
+  int dev = 0;
+  UGLAD_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= MAX_DEV) { set_error("device ordinal %d out of range", dev); return 1; }
+  if (!attr_set[dev]) {
+    UGLAD_CUDA(cudaFuncSetAttribute(tc_chain_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_RAW));
+    attr_set[dev] = true;
+  }
+  static ChainParams P;   // large (several KB): built in place under the lock below, copied by the launch
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  memset(&P, 0, sizeof(P));
+  P.nstages = c.nstages; P.M = P.N = P.K = c.D; P.batch = c.batch;
+  P.tiles_m = (c.D + tc::BM - 1) / tc::BM;
+  P.tiles_n = (c.D + BN - 1) / BN;
+  P.barrier = c.barrier;
+  P.dbg = g_tc_dbg;
+  for (int i = 0; i < c.nbuf; ++i) {
+    const TcChainBuf& b = c.buf[i];
+    const bool tma = b.ld % 4 == 0 && b.stride % 4 == 0 && (reinterpret_cast<uintptr_t>(b.ptr) & 15) == 0;
+    P.buf[i].ptr = b.ptr; P.buf[i].ld = b.ld; P.buf[i].stride = b.stride; P.buf[i].tma = tma ? 1 : 0;
+    if (tma) {
+      if (get_map(b.ptr, c.D, c.D, b.ld, c.batch, b.stride, tc::BM, &P.mapA[i])) return 1;
+      if (get_map(b.ptr, c.D, c.D, b.ld, c.batch, b.stride, BN, &P.mapB[i])) return 1;
+    }
+  }
+  int max_tiles = 0;
+  for (int s = 0; s < c.nstages; ++s) {
+    const TcChainStage& S = c.st[s];
+    P.st[s].nprob = S.nprob;
+    P.st[s].antisym = S.antisym;
+    for (int k = 0; k < S.nprob; ++k) {
+      const TcChainProb& q = S.p[k];
+      if (!P.buf[q.a].tma || !P.buf[q.b].tma) { set_error("tc_chain: operand buffers need 16-byte aligned rows"); return 1; }
+      P.st[s].p[k] = ChainProb{q.a, q.b, q.c, q.e1, q.alpha, q.beta, q.diag, q.alpha_dev};
+    }
+    const int tiles = P.tiles_m * P.tiles_n * c.batch * S.nprob;
+    if (tiles > max_tiles) max_tiles = tiles;
+  }
+  int nsm = 0;
+  if (num_sms(&nsm)) return 1;
+  const int grid = max_tiles < nsm ? max_tiles : nsm;
+  UGLAD_CUDA(cudaMemsetAsync(c.barrier, 0, sizeof(unsigned), st));
+  double flops = 0.0;
+  for (int s = 0; s < c.nstages; ++s) flops += 2.0 * c.D * c.D * c.D * c.batch * c.st[s].nprob;
+  profile_begin(st, 1, flops);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(tc::THREADS_RAW);
+  cfg.dynamicSmemBytes = C::SMEM_RAW;
+  cfg.stream = st;
+  cfg.attrs = nullptr;
+  cfg.numAttrs = 0;
+  UGLAD_CUDA(cudaLaunchKernelEx(&cfg, tc_chain_kernel<BN>, P));
+  profile_end(st);
+  UGLAD_CHECK_LAUNCH("tc_chain_kernel");
+  return 0;
+}
+
+int launch_tc_chain(const TcChain& c, cudaStream_t st) {
+  if (c.nstages <= 0 || c.nstages > tc::CH_MAX_STAGE || c.nbuf > tc::CH_MAX_BUF || !c.barrier) {
+    set_error("tc_chain: %d stages / %d buffers outside the kernel's limits", c.nstages, c.nbuf);
+    return 1;
+  }
+  int nsm = 0;
+  if (num_sms(&nsm)) return 1;
+  int bn = g_tc_chain_bn;
+  if (bn == 0) {
+    // wide tiles when a single-product stage still fills most of the SMs, narrow ones otherwise
+    const long long t128 = (long long)((c.D + 127) / 128) * ((c.D + 127) / 128) * c.batch;
+    bn = (t128 * 10 >= (long long)nsm * 8) ? 128 : 64;
+  }
+  return bn == 128 ? launch_chain_bn<128>(c, st) : launch_chain_bn<64>(c, st);
+}
 }  // namespace uglad

@@ -91,6 +91,20 @@ bool tc_gemm_supported(const TcGemm& g);
 int launch_tc_gemm(const TcGemm& g, int batch, cudaStream_t st);
 // two independent products of identical shape in ONE launch (twice the tiles for the persistent grid)
 int launch_tc_gemm2(const TcGemm& g1, const TcGemm& g2, int batch, cudaStream_t st);
+// persistent chain of dependent same-shape products (D x D x D, batched), one launch, grid barriers between stages
+struct TcChainProb { int a, b, c, e1; float alpha = 1.f, beta = 0.f, diag = 0.f; const float* alpha_dev = nullptr; };
+struct TcChainStage { int nprob = 1; int antisym = -1; TcChainProb p[2]; };
+struct TcChainBuf { float* ptr = nullptr; int ld = 0; long long stride = 0; };
+struct TcChain {
+  TcChainBuf buf[12];
+  TcChainStage st[40];
+  int nbuf = 0, nstages = 0, D = 0, batch = 0;
+  unsigned* barrier = nullptr;   // one device word, zeroed by the launcher
+};
+int launch_tc_chain(const TcChain& c, cudaStream_t st);
+bool tc_chain_enabled();
+int tc_tune_chain(int on);
+int tc_tune_chain_bn(int bn);
 int tc_tune_dual(int on);
 int tc_tune_bn(int bn);
 int tc_tune_pdl(int on);
@@ -143,8 +157,16 @@ int launch_add_diag(float* S, int B, int D, const float* add_dev, cudaStream_t s
 int elem_blocks_per_graph(int D);
 int rho_param_count(int H);
 
+// exchange buffers of the graph-sharded forward (uglad_peers in the C-ABI): device pointers to every rank's slots
+#define UGLAD_MAX_PEERS 8
+struct PeerSlots {
+  unsigned long long* slots[UGLAD_MAX_PEERS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int world = 1, rank = 0;
+  unsigned tag = 0;
+};
 int launch_lambda_step(int k, const float* params, int H, float lambda_init, int B_total,
-                       const float* normf, float* lam, float* lamfeat, cudaStream_t st);
+                       float* normf, float* lam, float* lamfeat, cudaStream_t st, const PeerSlots* peers = nullptr,
+                       int L = 0);
 int launch_z_update_fwd(const float* X, const float* S, const float* Tprev, const float* params,
                         int H, int B, int D, float* Z, float* part, float* normf_out,
                         unsigned* counter, cudaStream_t st);

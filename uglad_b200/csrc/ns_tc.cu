@@ -255,12 +255,13 @@ struct TcsBuf {
   float* scal;
   float* part;
   unsigned* counter;
+  unsigned* barrier;   // grid barrier word of the persistent chain launch
   int ldp;
   long long n2p;  // floats per split half: B * D * ldp
 };
 size_t ns_tc_scratch_floats(int B, int D) {
   const size_t n2p = al4t((size_t)B * D * ldp_of(D));
-  return 16 * n2p + al4t(3 * (size_t)B) + al4t((size_t)B * elem_blocks_per_graph(D)) + al4t(B);
+  return 16 * n2p + al4t(3 * (size_t)B) + al4t((size_t)B * elem_blocks_per_graph(D)) + al4t(B) + 4;
 }
 static TcsBuf tcs_carve(float* scratch, int B, int D) {
   TcsBuf s;
@@ -274,6 +275,7 @@ static TcsBuf tcs_carve(float* scratch, int B, int D) {
   s.scal = scratch + 16 * (size_t)s.n2p;
   s.part = s.scal + al4t(3 * (size_t)B);
   s.counter = reinterpret_cast<unsigned*>(s.part + al4t((size_t)B * elem_blocks_per_graph(D)));
+  s.barrier = s.counter + al4t(B);
   return s;
 }
 int ns_tc_scratch_init(float* scratch, int B, int D, cudaStream_t st) {
@@ -324,6 +326,39 @@ int ns_tc_theta_update_forward(const float* S, long long sS, const float* Theta,
   UGLAD_CHECK_LAUNCH("tcs_diag_fro_kernel");
   tcs_t0_kernel<<<grid, TCS_THREADS, 0, st>>>(A.hi, A.lo, s.scal, B, D, s.ldp, Z.hi, Z.lo);
   UGLAD_CHECK_LAUNCH("tcs_t0_kernel");
+  if (tc_chain_enabled() && b.lo == nullptr) {
+    // the ten iterations as ONE persistent launch: 19 stages separated by grid barriers
+    TcChain c;
+    c.D = D; c.batch = B; c.barrier = s.barrier;
+    const SplitMat mats[7] = {b, A, Z, T, Y, Y2, Z2};
+    for (int i = 0; i < 7; ++i) { c.buf[i].ptr = mats[i].hi; c.buf[i].ld = s.ldp; c.buf[i].stride = (long long)D * s.ldp; }
+    c.buf[7].ptr = X; c.buf[7].ld = D; c.buf[7].stride = (long long)D * D;
+    c.nbuf = 8;
+    int iY = 4, iY2 = 5, iZ = 2, iZ2 = 6;
+    const int ib = 0, iA = 1, iT = 3, iX = 7;
+    auto prob = [](int a, int bb, int cc, float alpha, float beta = 0.f, int e1 = -1, float diag = 0.f,
+                   const float* adev = nullptr) {
+      TcChainProb p; p.a = a; p.b = bb; p.c = cc; p.e1 = e1; p.alpha = alpha; p.beta = beta; p.diag = diag; p.alpha_dev = adev;
+      return p;
+    };
+    int ns = 0;
+    c.st[ns].nprob = 1; c.st[ns].p[0] = prob(iA, iZ, iY, 1.f, 0.f, -1, 0.f, s.scal + B); ++ns;
+    for (int t = 1; t < UGLAD_NS_ITERS; ++t) {
+      c.st[ns].nprob = 1; c.st[ns].p[0] = prob(iZ, iY, iT, -0.5f, 0.f, -1, 1.5f); ++ns;
+      if (t + 1 < UGLAD_NS_ITERS) {
+        c.st[ns].nprob = 2;
+        c.st[ns].p[0] = prob(iY, iT, iY2, 1.f);
+        c.st[ns].p[1] = prob(iT, iZ, iZ2, 1.f);
+        ++ns;
+        int tmp = iY; iY = iY2; iY2 = tmp;
+        tmp = iZ; iZ = iZ2; iZ2 = tmp;
+      } else {
+        c.st[ns].nprob = 1; c.st[ns].p[0] = prob(iY, iT, iX, 0.5f, -0.5f, ib, 0.f, s.scal + 2 * B); ++ns;
+      }
+    }
+    c.nstages = ns;
+    return launch_tc_chain(c, st);
+  }
   { TMM m; m.A = A; m.Bm = Z; m.C = Y; m.alpha_dev = s.scal + B; if (tmm(m, s, B, D, st)) return 1; }
   for (int t = 1; t < UGLAD_NS_ITERS; ++t) {
     { TMM m; m.A = Z; m.Bm = Y; m.C = T; m.alpha = -0.5f; m.diag = 1.5f; if (tmm(m, s, B, D, st)) return 1; }
@@ -355,6 +390,42 @@ int ns_tc_theta_update_backward(const float* S, long long sS, const float* Theta
   UGLAD_CHECK_LAUNCH("tcs_build_r_kernel");
   tcs_scale_aq_kernel<<<grid, TCS_THREADS, 0, st>>>(A.hi, A.lo, GX, s.scal, B, D, s.ldp, Q.hi, Q.lo);
   UGLAD_CHECK_LAUNCH("tcs_scale_aq_kernel");
+  if (tc_chain_enabled() && b.lo == nullptr) {
+    // the ten backward iterations as ONE persistent launch: per iteration {B3, P = A Q} | W <- P - P^T together
+    // with {Q B3, A B3 / 2} | {(Q B3 + A W^T) / 2}: 30 stages separated by grid barriers
+    TcChain c;
+    c.D = D; c.batch = B; c.barrier = s.barrier;
+    const SplitMat mats[8] = {b, A, A2, Q, Q2, B3, QB, W};
+    for (int i = 0; i < 8; ++i) { c.buf[i].ptr = mats[i].hi; c.buf[i].ld = s.ldp; c.buf[i].stride = (long long)D * s.ldp; }
+    c.nbuf = 8;
+    int iA = 1, iA2 = 2, iQ = 3, iQ2 = 4;
+    const int iB3 = 5, iQB = 6, iW = 7;
+    auto prob = [](int a, int bb, int cc, float alpha, float beta = 0.f, int e1 = -1, float diag = 0.f) {
+      TcChainProb p; p.a = a; p.b = bb; p.c = cc; p.e1 = e1; p.alpha = alpha; p.beta = beta; p.diag = diag;
+      return p;
+    };
+    int ns = 0;
+    for (int t = 0; t < UGLAD_NS_ITERS; ++t) {
+      const bool last = t + 1 == UGLAD_NS_ITERS;
+      c.st[ns].nprob = 2;
+      c.st[ns].p[0] = prob(iA, iA, iB3, -1.f, 0.f, -1, 3.f);
+      c.st[ns].p[1] = prob(iA, iQ, iW, 1.f);
+      ++ns;
+      c.st[ns].antisym = iW;
+      c.st[ns].nprob = last ? 1 : 2;
+      c.st[ns].p[0] = prob(iQ, iB3, iQB, 1.f);
+      if (!last) c.st[ns].p[1] = prob(iA, iB3, iA2, 0.5f);
+      ++ns;
+      c.st[ns].nprob = 1;
+      c.st[ns].p[0] = prob(iA, iW, iQ2, 0.5f, 0.5f, iQB);
+      ++ns;
+      if (!last) { int tmp = iA; iA = iA2; iA2 = tmp; }
+      int tmp = iQ; iQ = iQ2; iQ2 = tmp;
+    }
+    c.nstages = ns;
+    if (launch_tc_chain(c, st)) return 1;
+    Q = mats[iQ];
+  } else
   for (int t = 0; t < UGLAD_NS_ITERS; ++t) {
     {  // B3 = 3I - A A  and  P = A Q  (independent)
       TMM m1; m1.A = A; m1.Bm = A; m1.C = B3; m1.alpha = -1.f; m1.diag = 3.f;

@@ -211,6 +211,62 @@ def allreduce_min(t: torch.Tensor, group) -> torch.Tensor:
     return t
 
 
+class PeerExchange:
+    """Exchange buffers of the graph-sharded forward (uglad_glad_forward_sharded): one small device
+    buffer per rank, mapped into every rank of the box through CUDA IPC, so that the lambda kernels
+    exchange the per-layer Frobenius sums themselves (stores over NVLink) and the L layers of a shard
+    run as one uninterrupted stream of kernels -- no collective, no host code between the layers.
+    Built once per (group, L) with one all-gather of the 64-byte IPC handles."""
+
+    _cache: dict = {}
+    enabled = True
+
+    def __init__(self, group, L: int, device):
+        import torch.distributed as dist
+        lib = _lib.load()
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise _lib.UgladError("peer exchange serves up to 8 ranks of one box")
+        nbytes = lib.uglad_peer_slots_bytes(int(L))
+        ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+        check(lib.uglad_peer_alloc(nbytes, C.byref(ptr), handle), "uglad_peer_alloc")
+        mine = torch.tensor(list(handle.raw), dtype=torch.uint8, device=device)
+        every = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(every, mine, group=group)
+        self.slots = []
+        for r in range(self.world):
+            if r == self.rank:
+                self.slots.append(ptr.value)
+            else:
+                p = C.c_void_p()
+                check(lib.uglad_peer_open(bytes(every[r].cpu().tolist()), C.byref(p)), "uglad_peer_open")
+                self.slots.append(p.value)
+        self.tag = 0
+        dist.barrier(group=group)   # every rank has mapped every buffer before the first store
+
+    @classmethod
+    def get(cls, group, L: int, device):
+        key = (id(group), int(L), device.index)
+        if key not in cls._cache:
+            cls._cache[key] = cls(group, L, device)
+        return cls._cache[key]
+
+    def next_call(self) -> "_lib.UgladPeers":
+        self.tag = (self.tag + 1) & 0xFFFFFFFF or 1
+        p = _lib.UgladPeers()
+        p.world, p.rank, p.tag = self.world, self.rank, self.tag
+        for r, v in enumerate(self.slots):
+            p.slots[r] = v
+        return p
+
+
+def _use_peer_exchange(S: torch.Tensor, group) -> bool:
+    if not PeerExchange.enabled or group is None or not S.is_cuda:
+        return False
+    import torch.distributed as dist
+    return dist.get_backend(group) == "nccl" and dist.get_world_size(group) <= 8
+
+
 class GladFunction(torch.autograd.Function):
     """theta_pred = glad(S; params)  (glad.py:74-150) with the hand-written backward."""
 
@@ -244,6 +300,11 @@ class GladFunction(torch.autograd.Function):
         if world == 1:
             check(lib.uglad_glad_forward(C.byref(dims), _ptr(S), _ptr(flat_params), _ptr(wS), _ptr(VtS),
                                          _ptr(ws), _ptr(warm), st), "uglad_glad_forward")
+        elif _use_peer_exchange(S, group):
+            # one call: the ranks exchange the per-layer Frobenius sums through peer-mapped memory
+            peers = PeerExchange.get(group, L, S.device).next_call()
+            check(lib.uglad_glad_forward_sharded(C.byref(dims), _ptr(S), _ptr(flat_params), _ptr(wS), _ptr(VtS),
+                                                 _ptr(ws), _ptr(warm), C.byref(peers), st), "uglad_glad_forward_sharded")
         else:
             check(lib.uglad_glad_init_forward(C.byref(dims), _ptr(S), _ptr(flat_params), _ptr(wS), _ptr(VtS),
                                               _ptr(ws), st), "uglad_glad_init_forward")

@@ -62,6 +62,33 @@ def get_covariance(Xb, offset: float = 0.1, warm=None) -> torch.Tensor:
     return out
 
 
+def bind_host_to_device_numa(device=None) -> Optional[int]:
+    """Input-pipeline hygiene for multi-GPU boxes: restrict this process to the CPUs of the NUMA node
+    its GPU hangs off, so that pinned staging buffers allocated afterwards (first touch) and the
+    threads that fill them are local to the GPU's PCIe root -- with one process per GPU and all of
+    them streaming samples at once, cross-socket copies otherwise halve the host->device bandwidth.
+    Returns the node, or None when the topology cannot be read (nothing is changed then)."""
+    import os
+    try:
+        dev = _device() if device is None else device
+        pr = torch.cuda.get_device_properties(dev)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 class CovariancePrefetcher:
     """Input pipeline for repeated fits on fresh sample batches of one shape [B, M, D]: the
     host->device copy of the NEXT batch and its covariance + conditioning run on a side stream while
