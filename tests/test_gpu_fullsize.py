@@ -313,3 +313,30 @@ def test_peer_exchange_forward_reproduces_the_whole_batch(D, small_d_max):
                 assert edges_match(theta.cpu().numpy(), theta_all[sl].cpu().numpy())
     finally:
         ops.tune("small_d_max", 166)
+
+
+@pytest.mark.parametrize("B,D", [(2, 256), (4, 200), (1, 333)])
+def test_persistent_chain_launch_is_bit_identical_to_separate_launches(B, D):
+    """uglad_tune("tc_chain", 1): the ten Newton-Schulz iterations of a layer (forward: 19 stages, backward:
+    30 stages incl. the in-kernel antisymmetrisation) as ONE persistent launch with grid barriers.  Same
+    tiles, same arithmetic: theta, loss and gradients must equal the separate launches bit for bit --
+    also with fewer tiles than CTAs in a stage (idle CTAs must not run ahead of the barrier) and with a D
+    whose rows are not 16-byte multiples (direct-store epilogue)."""
+    from uglad_b200 import main as ug, ops
+    rng = np.random.default_rng(B * 1000 + D)
+    X = rng.random((B, 2 * D, D))
+    S = torch.tensor(O.covariance(X), dtype=torch.float32).cuda()
+    P_ = _low_threshold_params(9)
+    out = {}
+    for chain in (0, 1):
+        ops.tune("tc_chain", chain)
+        try:
+            model = _model_from(P_)
+            th, loss = ug.forward_uGLAD(S, model, L=3, INIT_DIAG=0)
+            loss.backward()
+            out[chain] = (th.detach().clone(), loss.detach().clone(),
+                          torch.cat([p.grad.reshape(-1) for p in model.parameters()]).clone())
+        finally:
+            ops.tune("tc_chain", 0)
+    for a, b in zip(out[0], out[1]):
+        assert torch.equal(a, b)

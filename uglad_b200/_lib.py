@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libuglad_b200.so")
+# UGLAD_B200_LIB: developer override (A/B of two builds of the library in one GPU session)
+LIB_PATH = os.environ.get("UGLAD_B200_LIB") or os.path.join(_HERE, "lib", "libuglad_b200.so")
 
 
 class UgladDims(C.Structure):

@@ -153,6 +153,7 @@ static int tc_mm(const float* Ah, const float* Al, const float* Bh, const float*
 }
 // eigenvector products on plain FP32 operands (hi/lo formed inside the tcgen05 kernel) instead of
 // pre-split pairs: uglad_tune("eig_raw", 1)
+static int g_eig_pre = 1;   // warm solves: U0 = G V_prev and the Rayleigh quotients as tcgen05 GEMMs outside the Jacobi kernel
 static int g_eig_raw = 1;
 static bool eig_raw() { return g_eig_raw && tc_raw_enabled(); }
 // C = alpha V diag(f) V^T + beta E1 on the tensor pipe: split / transpose the eigenvectors into
@@ -457,7 +458,28 @@ static int layer_forward_impl(const uglad_dims* d, int k, const float* S, const 
   a.warmVt = warm_ws ? warm_ws + w.Vt + (size_t)k * w.n2 : nullptr;
   a.warm_w = warm_ws ? warm_ws + w.beta + (size_t)k * w.n1 : nullptr;
   a.D = D; a.shift_mode = 1; a.tail = TAIL_LAYER; a.exact_sqrt = d->exact_sqrt;
-  if (launch_eig(a, B, st)) return 1;
+  if (warm_ws && g_eig_pre && ns_use_tc() && eig_raw() && D % 4 == 0 && D >= 16) {
+    // warm solve with its two D^3 products (U0 = G V_prev, Rayleigh quotients) on the tcgen05 GEMM: the Jacobi
+    // kernel is left with the sweeps and ONE shared-memory matrix (see eig_prep_kernel)
+    float* Gm = ws + w.sp + 2 * w.n2p;
+    float* U0 = ws + w.sp + 4 * w.n2p;     // then W = V^T G
+    float* sig = ws + w.f0;                // theta_0's scalars are dead once the layers run
+    float* tr = sig + B;
+    if (launch_eig_prep(S, (long long)D * D, theta_prev, ws + w.lam + k, a.warm_w, B, D, w.ldp, Gm, sig, tr, st)) return 1;
+    TcGemm g;
+    g.A_hi = a.warmVt; g.lda = D; g.sA = (long long)D * D;
+    g.B_hi = Gm; g.ldb = w.ldp; g.sB = (long long)D * w.ldp;
+    g.M = g.N = g.K = D;
+    g.C_hi = U0; g.ldc = w.ldp; g.sC = (long long)D * w.ldp;
+    if (launch_tc_gemm(g, B, st)) return 1;
+    a.U0 = U0; a.ldu = w.ldp; a.pre_sigma = sig; a.pre_trace = tr; a.tail = TAIL_PLAIN;
+    if (launch_eig(a, B, st)) return 1;
+    g.A_hi = Vk;
+    if (launch_tc_gemm(g, B, st)) return 1;   // W = V^T G' into the same buffer
+    if (launch_eig_rq_tail(U0, Vk, sig, ws + w.lam + k, B, D, w.ldp, d->exact_sqrt, a.w, fk, a.sroot, a.snorm, st)) return 1;
+  } else if (launch_eig(a, B, st)) {
+    return 1;
+  }
   if (ns_use_tc()) {  // X = (V diag f) V^T on the tensor pipe; the split eigenvectors are kept for the backward
     float* VtSk = ws + w.VtS + (size_t)k * 2 * w.n2p;
     float* VSk = ws + w.VS + (size_t)k * 2 * w.n2p;
@@ -764,6 +786,7 @@ int uglad_profile(int enable, double* total_ms, unsigned long long* launches) {
 int uglad_tune(const char* key, int value) {
   if (!key) return 1;
   if (!strcmp(key, "eig_raw")) { g_eig_raw = value ? 1 : 0; return 0; }
+  if (!strcmp(key, "eig_pre")) { g_eig_pre = value ? 1 : 0; return 0; }
   if (!strcmp(key, "small_d_max")) {
     if (value < 0 || value > UGLAD_SMALL_D_MAX) { set_error("small_d_max must lie in [0, %d]", UGLAD_SMALL_D_MAX); return 1; }
     g_small_d_max = value;

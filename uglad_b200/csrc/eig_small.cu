@@ -72,6 +72,22 @@ __device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.
 __device__ __forceinline__ float fast_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
+// packed FP32 pairs (sm_100 FFMA2: one issue slot, two FMAs): the sweeps are issue-bound, and the dot
+// products and rotations are nothing but FMAs on float4 chunks that already sit in aligned register pairs
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
 __device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
 }
@@ -236,6 +252,18 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
   float sigma = 0.f, trace = 0.f, wsum = 0.f;
   long long t_start = clock64(), t_sweeps0 = 0, t_sweeps1 = 0;
   for (int attempt = 0; attempt < 2; ++attempt) {
+    if (attempt == 0 && a.U0 != nullptr) {
+      // pre-multiplied warm start: U_0 = (A + sigma I) V_prev was formed by a tcgen05 GEMM; nothing else to set up
+      const float* U0b = a.U0 + (size_t)b * D * a.ldu;
+      for (int idx = tid; idx < D * ld; idx += nthreads) {
+        const int col = idx / ld, row = idx - col * ld;
+        U[idx] = (row < D) ? U0b[(size_t)col * a.ldu + row] : 0.f;
+      }
+      if (tid == 0) { s_flag = 0u; s_nfix = 0u; }
+      sigma = a.pre_sigma[b];
+      trace = a.pre_trace[b];
+      __syncthreads();
+    } else {
     // ---- load (coalesced along the contiguous global dimension) -------------------------
     float trace_part = 0.f, fro_part = 0.f;
     for (int idx = tid; idx < D * ld; idx += nthreads) {
@@ -378,6 +406,7 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
       }
       __syncthreads();
     }
+    }  // !pre
 
     // ---- Jacobi sweeps -------------------------------------------------------------------
     t_sweeps0 = clock64();
@@ -409,20 +438,23 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
         float* up = Ul + (size_t)p * ld;
         float* uq = Ul + (size_t)q * ld;
         float4 av[CH], bv[CH];
-        float g0 = 0.f, g1 = 0.f;   // two independent chains halve the dependent-FFMA latency
+        unsigned long long g01 = 0ull, g23 = 0ull;   // four independent chains in two packed accumulators
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
           if (PAD || gl + LP * c < nch) {
             av[c] = *reinterpret_cast<const float4*>(up + 4 * LP * c);
             bv[c] = *reinterpret_cast<const float4*>(uq + 4 * LP * c);
-            g0 = fmaf(av[c].x, bv[c].x, fmaf(av[c].y, bv[c].y, g0));
-            g1 = fmaf(av[c].z, bv[c].z, fmaf(av[c].w, bv[c].w, g1));
+            g01 = ffma2(pk2(av[c].x, av[c].y), pk2(bv[c].x, bv[c].y), g01);
+            g23 = ffma2(pk2(av[c].z, av[c].w), pk2(bv[c].z, bv[c].w), g23);
           } else {
             av[c] = make_float4(0.f, 0.f, 0.f, 0.f);
             bv[c] = av[c];
           }
         }
-        const float ga = group_sum<LP>(g0 + g1);
+        float g0, g1, g2, g3;
+        upk2(g01, g0, g1);
+        upk2(g23, g2, g3);
+        const float ga = group_sum<LP>((g0 + g1) + (g2 + g3));
         const float al = nrm2[p], be = nrm2[q];
         const float den = al * be;
         const float g2s = ga * ga;
@@ -438,14 +470,18 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
           cs = cs * fmaf(-0.5f * x, cs * cs, 1.5f);  // one Newton step: ~0.5 ulp
           const float sn = t * cs;
           const float tau = sn * fast_rcp(1.f + cs);
+          const unsigned long long tau2 = pk2(tau, tau), ntau2 = pk2(-tau, -tau), sn2 = pk2(sn, sn), nsn2 = pk2(-sn, -sn);
 #pragma unroll
           for (int c = 0; c < CH; ++c) {
             if (PAD || gl + LP * c < nch) {
+              const unsigned long long a01 = pk2(av[c].x, av[c].y), a23 = pk2(av[c].z, av[c].w);
+              const unsigned long long b01 = pk2(bv[c].x, bv[c].y), b23 = pk2(bv[c].z, bv[c].w);
+              // a' = a - s (b + tau a), b' = b + s (a - tau b): four packed FMAs per pair of rows
+              const unsigned long long na01 = ffma2(nsn2, ffma2(tau2, a01, b01), a01), na23 = ffma2(nsn2, ffma2(tau2, a23, b23), a23);
+              const unsigned long long nb01 = ffma2(sn2, ffma2(ntau2, b01, a01), b01), nb23 = ffma2(sn2, ffma2(ntau2, b23, a23), b23);
               float4 na, nb;
-              na.x = av[c].x - sn * fmaf(tau, av[c].x, bv[c].x);  nb.x = bv[c].x + sn * fmaf(-tau, bv[c].x, av[c].x);
-              na.y = av[c].y - sn * fmaf(tau, av[c].y, bv[c].y);  nb.y = bv[c].y + sn * fmaf(-tau, bv[c].y, av[c].y);
-              na.z = av[c].z - sn * fmaf(tau, av[c].z, bv[c].z);  nb.z = bv[c].z + sn * fmaf(-tau, bv[c].z, av[c].z);
-              na.w = av[c].w - sn * fmaf(tau, av[c].w, bv[c].w);  nb.w = bv[c].w + sn * fmaf(-tau, bv[c].w, av[c].w);
+              upk2(na01, na.x, na.y); upk2(na23, na.z, na.w);
+              upk2(nb01, nb.x, nb.y); upk2(nb23, nb.z, nb.w);
               *reinterpret_cast<float4*>(up + 4 * LP * c) = na;
               *reinterpret_cast<float4*>(uq + 4 * LP * c) = nb;
             }
@@ -521,16 +557,19 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
             const float al = nrm2[p];
             for (int q = p + 1; q < D; ++q) {
               const float* uq = Ul + (size_t)q * ld;
-              float g0 = 0.f, g1 = 0.f;
+              unsigned long long g01 = 0ull, g23 = 0ull;
 #pragma unroll
               for (int c = 0; c < CH; ++c) {
                 if (PAD || gl + LP * c < nch) {
                   const float4 bv = *reinterpret_cast<const float4*>(uq + 4 * LP * c);
-                  g0 = fmaf(av[c].x, bv.x, fmaf(av[c].y, bv.y, g0));
-                  g1 = fmaf(av[c].z, bv.z, fmaf(av[c].w, bv.w, g1));
+                  g01 = ffma2(pk2(av[c].x, av[c].y), pk2(bv.x, bv.y), g01);
+                  g23 = ffma2(pk2(av[c].z, av[c].w), pk2(bv.z, bv.w), g23);
                 }
               }
-              const float ga = group_sum_masked<LP>(g0 + g1, gmask);
+              float g0, g1, g2, g3;
+              upk2(g01, g0, g1);
+              upk2(g23, g2, g3);
+              const float ga = group_sum_masked<LP>((g0 + g1) + (g2 + g3), gmask);
               const float den = al * nrm2[q];
               if (ga * ga > tol2 * den) {
                 cmax = fmaxf(cmax, ga * ga / den);   // largest squared cosine above the tolerance
@@ -842,6 +881,7 @@ int launch_eig_small(const EigArgs& a_in, int B, cudaStream_t st) {
   const size_t extra = 2 * a.ld * sizeof(float) + 32 * sizeof(double) + 32 * sizeof(float) + 16;
   const bool fits2 = 2 * mat + extra <= 227 * 1024;
   a.keepG = (g_tune_keepg < 0) ? (fits2 ? 1 : 0) : (g_tune_keepg && fits2 ? 1 : 0);
+  if (a.U0 != nullptr) { a.keepG = 0; a.warmVt = nullptr; a.warm_w = nullptr; }   // pre-multiplied start: one buffer
   if (g_tune_tol_1e7 > 0) a.tol = 1e-7f * (float)g_tune_tol_1e7;
   if (!a.keepG) a.warmVt = nullptr;
   const size_t smem = (a.keepG ? 2 : 1) * mat + extra;

@@ -342,6 +342,119 @@ int launch_phi_split(float* Gh, float* Gl, const float* beta, const float* sroot
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// Warm-started theta update with the solver's two D^3 products on the tcgen05 GEMM instead of inside the
+// Jacobi kernel (api.cu: layer_forward_impl):
+//   eig_prep_kernel : G' = S/lambda - Theta_prev + sigma I  ([B][D][ldp]; sigma = 1.35 max|eigenvalues of the
+//                     previous epoch|, the solver's shift), sigma and trace(S/lambda - Theta_prev) per graph
+//   GEMM            : U0^T = V_prev^T G'   (row k = G' v_k: the solver's column-major start matrix)
+//   Jacobi kernel   : sweeps on U0 only (EigArgs::pre), eigenvectors out
+//   GEMM            : W = V^T G'
+//   eig_rq_tail_kernel : Rayleigh quotients beta_k = <W_k, v_k> / <v_k, v_k> - sigma, then f(beta) and the
+//                     Newton-Schulz scalars of glad.py:140-142 / torch_sqrtm.py:12-28 (the solver's TAIL_LAYER)
+// One block per graph.
+__global__ void __launch_bounds__(256) eig_prep_kernel(const float* __restrict__ S, long long sS,
+                                                       const float* __restrict__ Theta, const float* __restrict__ lam,
+                                                       const float* __restrict__ warm_w, int D, int ldp,
+                                                       float* __restrict__ G, float* __restrict__ sig, float* __restrict__ tr) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  float mx = 0.f;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) mx = fmaxf(mx, fabsf(warm_w[(size_t)b * D + i]));
+  float sigma = 1.35f * block_max(mx, red);
+  if (!(sigma > 0.f)) sigma = 1.0f;
+  const float il = 1.f / lam[0];
+  const float* Sb = S + (size_t)b * sS;
+  const float* Tb = Theta + (size_t)b * D * D;
+  float* Gb = G + (size_t)b * D * ldp;
+  float tpart = 0.f;
+  const int n = D * D;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int r = i / D, c = i - r * D;
+    float v = fmaf(il, Sb[i], -Tb[i]);
+    if (r == c) { tpart += v; v += sigma; }
+    Gb[(size_t)r * ldp + c] = v;
+  }
+  for (int i = threadIdx.x; i < D * (ldp - D); i += blockDim.x) {   // padding columns (read by the TMA boxes)
+    const int r = i / (ldp - D), c = D + i % (ldp - D);
+    Gb[(size_t)r * ldp + c] = 0.f;
+  }
+  const float t = block_sum(tpart, red);
+  if (threadIdx.x == 0) { sig[b] = sigma; tr[b] = t; }
+}
+int launch_eig_prep(const float* S, long long sS, const float* Theta, const float* lam, const float* warm_w, int B,
+                    int D, int ldp, float* G, float* sig, float* tr, cudaStream_t st) {
+  eig_prep_kernel<<<B, 256, 0, st>>>(S, sS, Theta, lam, warm_w, D, ldp, G, sig, tr);
+  UGLAD_CHECK_LAUNCH("eig_prep_kernel");
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) eig_rq_tail_kernel(const float* __restrict__ W, const float* __restrict__ Vt,
+                                                          const float* __restrict__ sig, const float* __restrict__ lam, int D,
+                                                          int ldp, int exact_sqrt, float* __restrict__ w_out,
+                                                          float* __restrict__ f, float* __restrict__ sroot,
+                                                          float* __restrict__ snorm) {
+  extern __shared__ float wv[];   // [D] eigenvalues
+  __shared__ double redd[32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const float sigma = sig[b];
+  const float* Wb = W + (size_t)b * D * ldp;
+  const float* Vb = Vt + (size_t)b * D * D;
+  for (int k = warp; k < D; k += nw) {
+    float num = 0.f, den = 0.f;
+    for (int j = lane; j < D; j += 32) {
+      const float v = Vb[(size_t)k * D + j];
+      num = fmaf(Wb[(size_t)k * ldp + j], v, num);
+      den = fmaf(v, v, den);
+    }
+    num = warp_sum(num);
+    den = warp_sum(den);
+    if (lane == 0) {
+      const float ev = ((den > 0.f) ? num / den : 0.f) - sigma;
+      wv[k] = ev;
+      w_out[(size_t)b * D + k] = ev;
+    }
+  }
+  __syncthreads();
+  const double c4 = 4.0 / (double)lam[0];
+  double part = 0.0;
+  for (int i = tid; i < D; i += blockDim.x) {
+    const double be = wv[i];
+    const double mu = be * be + c4;
+    part += mu * mu;
+  }
+  const double nrm = sqrt(block_sum_d(part, redd));
+  double part2 = 0.0;
+  for (int i = tid; i < D; i += blockDim.x) {
+    const double be = wv[i];
+    const double mu = be * be + c4;
+    double sv;
+    if (exact_sqrt) {
+      sv = sqrt(mu);
+    } else {
+      double y = mu / nrm, z = 1.0;
+#pragma unroll
+      for (int t = 0; t < UGLAD_NS_ITERS; ++t) {
+        const double T = 0.5 * (3.0 - z * y);
+        y = y * T;
+        z = T * z;
+      }
+      sv = y * sqrt(nrm);
+    }
+    sroot[(size_t)b * D + i] = (float)sv;
+    f[(size_t)b * D + i] = (float)(0.5 * (sv - be));
+    part2 += sv * sv;
+  }
+  const double sn = sqrt(block_sum_d(part2, redd));
+  if (tid == 0) snorm[b] = (float)sn;
+}
+int launch_eig_rq_tail(const float* W, const float* Vt, const float* sig, const float* lam, int B, int D, int ldp,
+                       int exact_sqrt, float* w_out, float* f, float* sroot, float* snorm, cudaStream_t st) {
+  eig_rq_tail_kernel<<<B, 256, (size_t)D * sizeof(float), st>>>(W, Vt, sig, lam, D, ldp, exact_sqrt, w_out, f, sroot, snorm);
+  UGLAD_CHECK_LAUNCH("eig_rq_tail_kernel");
+  return 0;
+}
+
 // Eigenvectors for the tcgen05 products: Vt [B][D][D] (row k = eigenvector k) ->
 //   Vt split, V = Vt^T split, and (optionally) VF = V diag(f) split, all [B][D][ldp].
 // 32x32 tiles through shared memory, block (32, 8).

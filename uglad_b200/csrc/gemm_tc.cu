@@ -1307,7 +1307,8 @@ int launch_tc_gemm2(const TcGemm& g1, const TcGemm& g2, int batch, cudaStream_t 
 
 
 // ---- host side of the persistent chain ----------------------------------------------------------
-static int g_tc_chain = 1;      // 1 (default): the Newton-Schulz iterations run as one persistent chain launch
+static int g_tc_chain = 0;      // 1: the Newton-Schulz iterations run as one persistent chain launch (measured slower than the
+                                // PDL-chained launches while the main loop is shared-memory-bound: DESIGN.md)
 static int g_tc_chain_bn = 0;   // 0 auto / 64 / 128
 int tc_tune_chain(int on) { g_tc_chain = on ? 1 : 0; return 0; }
 int tc_tune_chain_bn(int bn) { g_tc_chain_bn = bn; return 0; }

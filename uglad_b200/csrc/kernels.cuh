@@ -24,6 +24,13 @@ struct EigArgs {
   float* scratch = nullptr;      // large-D path only
   const float* warmVt = nullptr; // optional [B][D][D] eigenvectors of a nearby matrix (warm start)
   const float* warm_w = nullptr; // optional [B][D] eigenvalues of that matrix (replaces the norm estimate)
+  // pre-multiplied warm start (the two D^3 products of the warm solve run as tcgen05 GEMMs outside the kernel):
+  // U0 [B][D][ldu], row k = (A + sigma I) v_k of the previous eigenvectors; sigma / trace(A) per graph.  The
+  // kernel then needs ONE shared-memory matrix and returns eigenvectors + column-norm eigenvalues only.
+  const float* U0 = nullptr;
+  const float* pre_sigma = nullptr;
+  const float* pre_trace = nullptr;
+  int ldu = 0;
   int keepG = 0;                 // set by the launcher: second shared-memory buffer holds A + sigma I
   int D = 0, ld = 0, build = 0, shift_mode = 1, tail = TAIL_PLAIN, exact_sqrt = 0;
   int max_sweeps = 40;
@@ -175,6 +182,10 @@ int launch_z_update_bwd(const float* GZ, const float* X, const float* S, const f
                         float* rho_part, cudaStream_t st, float* GXlo = nullptr, int ldp = 0);
 int launch_phi_split(float* Gh, float* Gl, const float* beta, const float* sroot, const float* snorm,
                      int exact_sqrt, int B, int D, int ldp, float* trh_part, cudaStream_t st);
+int launch_eig_prep(const float* S, long long sS, const float* Theta, const float* lam, const float* warm_w, int B,
+                    int D, int ldp, float* G, float* sig, float* tr, cudaStream_t st);
+int launch_eig_rq_tail(const float* W, const float* Vt, const float* sig, const float* lam, int B, int D, int ldp,
+                       int exact_sqrt, float* w_out, float* f, float* sroot, float* snorm, cudaStream_t st);
 int launch_eigvec_split(const float* Vt, const float* f, int B, int D, int ldp, float* Th, float* Tl, float* Vh,
                         float* Vl, float* Fh, float* Fl, cudaStream_t st);
 bool ns_use_tc();

@@ -219,7 +219,7 @@ class PeerExchange:
     Built once per (group, L) with one all-gather of the 64-byte IPC handles."""
 
     _cache: dict = {}
-    enabled = True
+    enabled = __import__("os").environ.get("UGLAD_PEER_EXCHANGE", "1") != "0"   # 0: per-layer NCCL all-reduce instead
 
     def __init__(self, group, L: int, device):
         import torch.distributed as dist
