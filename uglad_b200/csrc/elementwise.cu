@@ -96,7 +96,7 @@ template <int HT>
 __global__ void __launch_bounds__(EW_THREADS) z_update_fwd_kernel(
     const float* __restrict__ X, const float* __restrict__ S, const float* __restrict__ Tprev,
     const float* __restrict__ params, int H, int n, float* __restrict__ Z, float* part,
-    float* normf_out, unsigned* counter) {
+    float* normf_out, unsigned* counter, int vec4) {
   __shared__ float sw[1 + UGLAD_MAX_H * (UGLAD_NF + 4 + UGLAD_MAX_H) + 1 + 64];
   __shared__ float red[32];
   __shared__ double redd[32];
@@ -107,6 +107,28 @@ __global__ void __launch_bounds__(EW_THREADS) z_update_fwd_kernel(
   const size_t base = (size_t)blockIdx.y * n;
   float acc = 0.f;
   float h1[RhoMLP<HT>::HM], h2[RhoMLP<HT>::HM];
+  if (vec4) {
+    // four entries per thread and iteration: 16-byte loads / stores, and four independent MLP evaluations in
+    // flight (each is a dependent chain of FMAs and MUFU activations: one per thread left the kernel latency-bound)
+    const float4* X4 = reinterpret_cast<const float4*>(X + base);
+    const float4* S4 = reinterpret_cast<const float4*>(S + base);
+    const float4* T4 = reinterpret_cast<const float4*>(Tprev + base);
+    float4* Z4 = reinterpret_cast<float4*>(Z + base);
+    float acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    float g1[RhoMLP<HT>::HM], g2[RhoMLP<HT>::HM], k1[RhoMLP<HT>::HM], k2[RhoMLP<HT>::HM], m1[RhoMLP<HT>::HM], m2[RhoMLP<HT>::HM];
+    for (int i = blockIdx.x * EW_THREADS + threadIdx.x; i < n / 4; i += gridDim.x * EW_THREADS) {
+      const float4 x = X4[i], sv = S4[i], t = T4[i];
+      float4 z;
+      z.x = soft_threshold(x.x, mlp.forward(x.x, sv.x, t.x, h1, h2));
+      z.y = soft_threshold(x.y, mlp.forward(x.y, sv.y, t.y, g1, g2));
+      z.z = soft_threshold(x.z, mlp.forward(x.z, sv.z, t.z, k1, k2));
+      z.w = soft_threshold(x.w, mlp.forward(x.w, sv.w, t.w, m1, m2));
+      Z4[i] = z;
+      const float d0 = z.x - x.x, d1 = z.y - x.y, d2 = z.z - x.z, d3 = z.w - x.w;
+      acc = fmaf(d0, d0, acc); acc1 = fmaf(d1, d1, acc1); acc2 = fmaf(d2, d2, acc2); acc3 = fmaf(d3, d3, acc3);
+    }
+    acc = (acc + acc1) + (acc2 + acc3);
+  } else {
   for (int i = blockIdx.x * EW_THREADS + threadIdx.x; i < n; i += gridDim.x * EW_THREADS) {
     const float x = X[base + i];
     const float rho = mlp.forward(x, S[base + i], Tprev[base + i], h1, h2);
@@ -114,6 +136,7 @@ __global__ void __launch_bounds__(EW_THREADS) z_update_fwd_kernel(
     Z[base + i] = z;
     const float d = z - x;
     acc = fmaf(d, d, acc);
+  }
   }
   const float tot = block_sum(acc, red);
   const unsigned nblocks = gridDim.x * gridDim.y;
@@ -140,10 +163,12 @@ int launch_z_update_fwd(const float* X, const float* S, const float* Tprev, cons
                         unsigned* counter, cudaStream_t st) {
   dim3 grid(elem_blocks_per_graph(D), B);
   const int n = D * D;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const int vec4 = (n % 4 == 0 && al16(X) && al16(S) && al16(Tprev) && al16(Z)) ? 1 : 0;
   if (H == 3)
-    z_update_fwd_kernel<3><<<grid, EW_THREADS, 0, st>>>(X, S, Tprev, params, H, n, Z, part, normf_out, counter);
+    z_update_fwd_kernel<3><<<grid, EW_THREADS, 0, st>>>(X, S, Tprev, params, H, n, Z, part, normf_out, counter, vec4);
   else
-    z_update_fwd_kernel<0><<<grid, EW_THREADS, 0, st>>>(X, S, Tprev, params, H, n, Z, part, normf_out, counter);
+    z_update_fwd_kernel<0><<<grid, EW_THREADS, 0, st>>>(X, S, Tprev, params, H, n, Z, part, normf_out, counter, 0);
   UGLAD_CHECK_LAUNCH("z_update_fwd_kernel");
   return 0;
 }
@@ -157,7 +182,7 @@ template <int HT>
 __global__ void __launch_bounds__(EW_THREADS) z_update_bwd_kernel(
     const float* __restrict__ GZ, const float* __restrict__ X, const float* __restrict__ S,
     const float* __restrict__ Tprev, const float* __restrict__ params, int H, int n,
-    float* __restrict__ GX, float* __restrict__ GF3, float* rho_part, float* __restrict__ GXlo, int D, int ldp) {
+    float* __restrict__ GX, float* __restrict__ GF3, float* rho_part, float* __restrict__ GXlo, int D, int ldp, int vec4) {
   constexpr int HM = RhoMLP<HT>::HM;
   constexpr int NPR_MAX = HM * UGLAD_NF + HM + HM * HM + HM + HM + 1;
   __shared__ float sw[1 + UGLAD_MAX_H * (UGLAD_NF + 4 + UGLAD_MAX_H) + 1 + 64];
@@ -174,11 +199,11 @@ __global__ void __launch_bounds__(EW_THREADS) z_update_bwd_kernel(
   const int oW1 = 0, ob1 = Hh * UGLAD_NF, oW2 = ob1 + Hh, ob2 = oW2 + Hh * Hh, oW3 = ob2 + Hh, ob3 = oW3 + Hh;
   const size_t base = (size_t)blockIdx.y * n;
   float h1[HM], h2[HM], d2[HM], d1[HM];
-  for (int i = blockIdx.x * EW_THREADS + threadIdx.x; i < n; i += gridDim.x * EW_THREADS) {
-    const float x = X[base + i], s = S[base + i], t = Tprev[base + i], gz = GZ[base + i];
-    const float rho = mlp.forward(x, s, t, h1, h2);
+  // one entry: forward MLP, then (where the threshold is active and a gradient arrives) its backward
+  auto entry = [&](float x, float s, float t, float gz, float rho, const float* h1, const float* h2, float& gx, float& gt) {
     const bool act = (fabsf(x) - rho) > 0.f;
-    float gx = 0.f, gt = 0.f;
+    gx = 0.f;
+    gt = 0.f;
     if (act && gz != 0.f) {
       const float sgn = (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f);
       const float go = -sgn * gz * rho * (1.f - rho);  // grad wrt the pre-sigmoid output
@@ -216,6 +241,36 @@ __global__ void __launch_bounds__(EW_THREADS) z_update_bwd_kernel(
       gx = gz + fx;
       gt = ft;
     }
+  };
+  if (vec4) {
+    // four entries per iteration: 16-byte accesses and the four forward MLPs (the long MUFU chains) in flight together
+    const float4* X4 = reinterpret_cast<const float4*>(X + base);
+    const float4* S4 = reinterpret_cast<const float4*>(S + base);
+    const float4* T4 = reinterpret_cast<const float4*>(Tprev + base);
+    const float4* G4 = reinterpret_cast<const float4*>(GZ + base);
+    float4* GX4 = reinterpret_cast<float4*>(GX + base);
+    float4* GT4 = reinterpret_cast<float4*>(GF3 + base);
+    float a1[HM], a2[HM], b1[HM], b2[HM], c1[HM], c2[HM];
+    for (int i = blockIdx.x * EW_THREADS + threadIdx.x; i < n / 4; i += gridDim.x * EW_THREADS) {
+      const float4 x = X4[i], sv = S4[i], t = T4[i], gz = G4[i];
+      const float r0 = mlp.forward(x.x, sv.x, t.x, h1, h2);
+      const float r1 = mlp.forward(x.y, sv.y, t.y, a1, a2);
+      const float r2 = mlp.forward(x.z, sv.z, t.z, b1, b2);
+      const float r3 = mlp.forward(x.w, sv.w, t.w, c1, c2);
+      float4 gx, gt;
+      entry(x.x, sv.x, t.x, gz.x, r0, h1, h2, gx.x, gt.x);
+      entry(x.y, sv.y, t.y, gz.y, r1, a1, a2, gx.y, gt.y);
+      entry(x.z, sv.z, t.z, gz.z, r2, b1, b2, gx.z, gt.z);
+      entry(x.w, sv.w, t.w, gz.w, r3, c1, c2, gx.w, gt.w);
+      GX4[i] = gx;
+      GT4[i] = gt;
+    }
+  } else {
+  for (int i = blockIdx.x * EW_THREADS + threadIdx.x; i < n; i += gridDim.x * EW_THREADS) {
+    const float x = X[base + i], s = S[base + i], t = Tprev[base + i], gz = GZ[base + i];
+    const float rho = mlp.forward(x, s, t, h1, h2);
+    float gx, gt;
+    entry(x, s, t, gz, rho, h1, h2, gx, gt);
     if (ldp) {  // padded [B][D][ldp] layout the tcgen05 products read: a (hi, lo) pair, or plain (GXlo == nullptr)
       const int r = i / D, c = i - r * D;
       const size_t o = (size_t)blockIdx.y * D * ldp + (size_t)r * ldp + c;
@@ -231,6 +286,7 @@ __global__ void __launch_bounds__(EW_THREADS) z_update_bwd_kernel(
       GX[base + i] = gx;
     }
     GF3[base + i] = gt;
+  }
   }
   // block reduction of the NPR accumulators: shuffles inside each warp first, ONE barrier, then a
   // fixed-order sum over the warps (deterministic)
@@ -258,10 +314,14 @@ int launch_z_update_bwd(const float* GZ, const float* X, const float* S, const f
                         float* rho_part, cudaStream_t st, float* GXlo, int ldp) {
   dim3 grid(elem_blocks_per_graph(D), B);
   const int n = D * D;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  // the padded output layout is the contiguous one when D is a multiple of 4 (ldp == D)
+  const int vec4 = (n % 4 == 0 && (ldp == 0 || ldp == D) && GXlo == nullptr && al16(GZ) && al16(X) && al16(S) && al16(Tprev) &&
+                    al16(GX) && al16(GF3)) ? 1 : 0;
   if (H == 3)
-    z_update_bwd_kernel<3><<<grid, EW_THREADS, 0, st>>>(GZ, X, S, Tprev, params, H, n, GX, GF3, rho_part, GXlo, D, ldp);
+    z_update_bwd_kernel<3><<<grid, EW_THREADS, 0, st>>>(GZ, X, S, Tprev, params, H, n, GX, GF3, rho_part, GXlo, D, ldp, vec4);
   else
-    z_update_bwd_kernel<0><<<grid, EW_THREADS, 0, st>>>(GZ, X, S, Tprev, params, H, n, GX, GF3, rho_part, GXlo, D, ldp);
+    z_update_bwd_kernel<0><<<grid, EW_THREADS, 0, st>>>(GZ, X, S, Tprev, params, H, n, GX, GF3, rho_part, GXlo, D, ldp, 0);
   UGLAD_CHECK_LAUNCH("z_update_bwd_kernel");
   return 0;
 }
@@ -357,39 +417,49 @@ __global__ void __launch_bounds__(256) eig_prep_kernel(const float* __restrict__
                                                        const float* __restrict__ Theta, const float* __restrict__ lam,
                                                        const float* __restrict__ warm_w, int D, int ldp,
                                                        float* __restrict__ G, float* __restrict__ sig, float* __restrict__ tr) {
+  // grid (blocks per graph, B); D % 4 == 0 (so ldp == D): 16-byte accesses throughout
   __shared__ float red[32];
-  const int b = blockIdx.x;
+  const int b = blockIdx.y;
   float mx = 0.f;
   for (int i = threadIdx.x; i < D; i += blockDim.x) mx = fmaxf(mx, fabsf(warm_w[(size_t)b * D + i]));
-  float sigma = 1.35f * block_max(mx, red);
+  float sigma = 1.35f * block_max(mx, red);   // every block of the graph forms the same shift
   if (!(sigma > 0.f)) sigma = 1.0f;
   const float il = 1.f / lam[0];
   const float* Sb = S + (size_t)b * sS;
   const float* Tb = Theta + (size_t)b * D * D;
   float* Gb = G + (size_t)b * D * ldp;
-  float tpart = 0.f;
-  const int n = D * D;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int r = i / D, c = i - r * D;
-    float v = fmaf(il, Sb[i], -Tb[i]);
-    if (r == c) { tpart += v; v += sigma; }
-    Gb[(size_t)r * ldp + c] = v;
+  const float4* S4 = reinterpret_cast<const float4*>(Sb);
+  const float4* T4 = reinterpret_cast<const float4*>(Tb);
+  float4* G4 = reinterpret_cast<float4*>(Gb);
+  const int n4 = D * D / 4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const float4 sv = S4[i], tv = T4[i];
+    float4 v = make_float4(fmaf(il, sv.x, -tv.x), fmaf(il, sv.y, -tv.y), fmaf(il, sv.z, -tv.z), fmaf(il, sv.w, -tv.w));
+    const int e = 4 * i, r = e / D, c = e - r * D;   // the four entries share row r (D % 4 == 0)
+    const int dc = r - c;                            // position of the diagonal inside the float4, if any
+    if (dc == 0) v.x += sigma; else if (dc == 1) v.y += sigma; else if (dc == 2) v.z += sigma; else if (dc == 3) v.w += sigma;
+    G4[i] = v;
   }
-  for (int i = threadIdx.x; i < D * (ldp - D); i += blockDim.x) {   // padding columns (read by the TMA boxes)
-    const int r = i / (ldp - D), c = D + i % (ldp - D);
-    Gb[(size_t)r * ldp + c] = 0.f;
+  if (blockIdx.x == 0) {   // trace of S/lambda - Theta_prev (the solver checks sum of its column norms against it)
+    float tpart = 0.f;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) tpart += fmaf(il, Sb[(size_t)i * D + i], -Tb[(size_t)i * D + i]);
+    const float t = block_sum(tpart, red);
+    if (threadIdx.x == 0) { sig[b] = sigma; tr[b] = t; }
   }
-  const float t = block_sum(tpart, red);
-  if (threadIdx.x == 0) { sig[b] = sigma; tr[b] = t; }
 }
 int launch_eig_prep(const float* S, long long sS, const float* Theta, const float* lam, const float* warm_w, int B,
                     int D, int ldp, float* G, float* sig, float* tr, cudaStream_t st) {
-  eig_prep_kernel<<<B, 256, 0, st>>>(S, sS, Theta, lam, warm_w, D, ldp, G, sig, tr);
+  if (D % 4 != 0 || ldp != D) { set_error("eig_prep: D must be a multiple of 4"); return 1; }
+  int pb = (D * D / 4 + 255 * 4) / (256 * 4);   // ~4 float4 per thread
+  if (pb < 1) pb = 1;
+  if (pb > 64) pb = 64;
+  dim3 grid(pb, B);
+  eig_prep_kernel<<<grid, 256, 0, st>>>(S, sS, Theta, lam, warm_w, D, ldp, G, sig, tr);
   UGLAD_CHECK_LAUNCH("eig_prep_kernel");
   return 0;
 }
 
-__global__ void __launch_bounds__(256) eig_rq_tail_kernel(const float* __restrict__ W, const float* __restrict__ Vt,
+__global__ void __launch_bounds__(512) eig_rq_tail_kernel(const float* __restrict__ W, const float* __restrict__ Vt,
                                                           const float* __restrict__ sig, const float* __restrict__ lam, int D,
                                                           int ldp, int exact_sqrt, float* __restrict__ w_out,
                                                           float* __restrict__ f, float* __restrict__ sroot,
@@ -402,10 +472,12 @@ __global__ void __launch_bounds__(256) eig_rq_tail_kernel(const float* __restric
   const float* Vb = Vt + (size_t)b * D * D;
   for (int k = warp; k < D; k += nw) {
     float num = 0.f, den = 0.f;
-    for (int j = lane; j < D; j += 32) {
-      const float v = Vb[(size_t)k * D + j];
-      num = fmaf(Wb[(size_t)k * ldp + j], v, num);
-      den = fmaf(v, v, den);
+    const float4* V4 = reinterpret_cast<const float4*>(Vb + (size_t)k * D);      // D % 4 == 0: 16-byte rows
+    const float4* W4 = reinterpret_cast<const float4*>(Wb + (size_t)k * ldp);
+    for (int j = lane; j < D / 4; j += 32) {
+      const float4 v = V4[j], w4 = W4[j];
+      num = fmaf(w4.x, v.x, fmaf(w4.y, v.y, fmaf(w4.z, v.z, fmaf(w4.w, v.w, num))));
+      den = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, den))));
     }
     num = warp_sum(num);
     den = warp_sum(den);
@@ -450,7 +522,7 @@ __global__ void __launch_bounds__(256) eig_rq_tail_kernel(const float* __restric
 }
 int launch_eig_rq_tail(const float* W, const float* Vt, const float* sig, const float* lam, int B, int D, int ldp,
                        int exact_sqrt, float* w_out, float* f, float* sroot, float* snorm, cudaStream_t st) {
-  eig_rq_tail_kernel<<<B, 256, (size_t)D * sizeof(float), st>>>(W, Vt, sig, lam, D, ldp, exact_sqrt, w_out, f, sroot, snorm);
+  eig_rq_tail_kernel<<<B, 512, (size_t)D * sizeof(float), st>>>(W, Vt, sig, lam, D, ldp, exact_sqrt, w_out, f, sroot, snorm);
   UGLAD_CHECK_LAUNCH("eig_rq_tail_kernel");
   return 0;
 }
