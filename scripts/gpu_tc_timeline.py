@@ -8,6 +8,7 @@ M, N, K, batch = (int(v) for v in sys.argv[1:5])
 bn = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 ops.tune("tc_bn", bn)
 ops.tune("tc_raw", int(os.environ.get("TC_RAW", "1")))
+ops.tune("tc_atm", int(os.environ.get("TC_ATM", "1")))
 A = torch.randn(batch, M, K, device=dev); B = torch.randn(batch, N, K, device=dev)
 out = torch.empty(batch, M, N, device=dev)
 scratch = torch.empty(lib.uglad_tc_gemm_scratch_floats(M, N, K, batch), device=dev)

@@ -370,6 +370,40 @@ __global__ void __launch_bounds__(EW_THREADS) phi_split_kernel(
   const float* sr = sroot + (size_t)b * D;
   const float inv_nrm = 1.f / snorm[b];
   float tr = 0.f;
+  if (Gl == nullptr && !exact_sqrt && D % 4 == 0 && ldp == D) {
+    // four neighbours of one row per thread: 16-byte accesses, and four independent ten-step recurrences in
+    // flight (one per thread left the kernel latency-bound); the row's own sequence a_i is shared by the four
+    float4* G4 = reinterpret_cast<float4*>(Gh + (size_t)b * n);
+    for (int q = blockIdx.x * EW_THREADS + threadIdx.x; q < n / 4; q += gridDim.x * EW_THREADS) {
+      const int e = 4 * q, i = e / D, j = e - i * D;
+      float4 g = G4[q];
+      float ai = sr[i] * inv_nrm;
+      float a0 = sr[j] * inv_nrm, a1 = sr[j + 1] * inv_nrm, a2 = sr[j + 2] * inv_nrm, a3 = sr[j + 3] * inv_nrm;
+      float c0 = 1.f, c1 = 1.f, c2 = 1.f, c3 = 1.f;
+#pragma unroll
+      for (int t = 0; t < UGLAD_NS_ITERS; ++t) {
+        const float base = 3.f - ai * ai;
+        c0 *= 0.5f * (base - a0 * a0 + ai * a0);
+        c1 *= 0.5f * (base - a1 * a1 + ai * a1);
+        c2 *= 0.5f * (base - a2 * a2 + ai * a2);
+        c3 *= 0.5f * (base - a3 * a3 + ai * a3);
+        ai = 0.5f * ai * (3.f - ai * ai);
+        a0 = 0.5f * a0 * (3.f - a0 * a0);
+        a1 = 0.5f * a1 * (3.f - a1 * a1);
+        a2 = 0.5f * a2 * (3.f - a2 * a2);
+        a3 = 0.5f * a3 * (3.f - a3 * a3);
+      }
+      const float bi = be[i], k = 0.25f * inv_nrm;   // H = 0.5 C g with C = 0.5 c / ||s||
+      const float h0 = k * c0 * g.x, h1 = k * c1 * g.y, h2 = k * c2 * g.z, h3 = k * c3 * g.w;
+      const int dj = i - j;
+      if (dj == 0) tr += h0; else if (dj == 1) tr += h1; else if (dj == 2) tr += h2; else if (dj == 3) tr += h3;
+      g.x = (bi + be[j]) * h0 - 0.5f * g.x;
+      g.y = (bi + be[j + 1]) * h1 - 0.5f * g.y;
+      g.z = (bi + be[j + 2]) * h2 - 0.5f * g.z;
+      g.w = (bi + be[j + 3]) * h3 - 0.5f * g.w;
+      G4[q] = g;
+    }
+  } else
   for (int idx = blockIdx.x * EW_THREADS + threadIdx.x; idx < n; idx += gridDim.x * EW_THREADS) {
     const int i = idx / D, j = idx - i * D;
     const size_t o = (size_t)b * D * ldp + (size_t)i * ldp + j;
@@ -604,6 +638,21 @@ __global__ void __launch_bounds__(EW_THREADS) gb_finish_kernel(
   __shared__ float red[32];
   const size_t base = (size_t)blockIdx.y * n;
   float acc = 0.f;
+  if (n % 4 == 0 && ((reinterpret_cast<uintptr_t>(Gb) | reinterpret_cast<uintptr_t>(GF3) | reinterpret_cast<uintptr_t>(S) |
+                      reinterpret_cast<uintptr_t>(Gnext)) & 15) == 0) {
+    const float4* Gb4 = reinterpret_cast<const float4*>(Gb + base);
+    const float4* F4 = reinterpret_cast<const float4*>(GF3 + base);
+    const float4* S4 = reinterpret_cast<const float4*>(S + base);
+    float4* N4 = reinterpret_cast<float4*>(Gnext + base);
+    float acc1 = 0.f;
+    for (int i = blockIdx.x * EW_THREADS + threadIdx.x; i < n / 4; i += gridDim.x * EW_THREADS) {
+      const float4 gb = Gb4[i], sv = S4[i], f = F4[i];
+      acc = fmaf(sv.x, gb.x, fmaf(sv.y, gb.y, acc));
+      acc1 = fmaf(sv.z, gb.z, fmaf(sv.w, gb.w, acc1));
+      N4[i] = make_float4(f.x - gb.x, f.y - gb.y, f.z - gb.z, f.w - gb.w);
+    }
+    acc += acc1;
+  } else
   for (int i = blockIdx.x * EW_THREADS + threadIdx.x; i < n; i += gridDim.x * EW_THREADS) {
     const float gb = Gb[base + i];
     acc = fmaf(S[base + i], gb, acc);

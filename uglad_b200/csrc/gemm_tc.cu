@@ -181,6 +181,30 @@ __device__ __forceinline__ void tmem_ld32x2(uint32_t taddr, uint32_t off, uint32
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 32 consecutive 32-bit columns of this thread's TMEM lane (the warp owns lanes 32 (warp % 4) ...)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]^T: the A operand (128 lanes x 8 columns of 32-bit TF32 containers) comes from
+// tensor memory, so it costs no shared-memory bandwidth
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
 template <int BN>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 4;
@@ -516,7 +540,22 @@ __device__ __forceinline__ void tc_issue_slab(uint64_t d0, uint32_t tmem_d, int 
   }
 }
 
-template <int BN, bool RAW>
+// the same with the A operand in tensor memory (ATM kernels): hi at tmem_a, lo 32 columns further
+template <int BN, int OFF>
+__device__ __forceinline__ void tc_issue_slab_ts(uint64_t d0, uint32_t tmem_d, uint32_t tmem_a, int ngran, bool first_slab) {
+  using C = tc::Cfg<BN>;
+  constexpr uint64_t oBh = (uint64_t)((OFF + 2 * tc::A_BYTES) >> 4);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    if (g < ngran) {
+      const uint64_t adv = (uint64_t)(g * 2);
+      tc::umma_tf32_ts(tmem_d, tmem_a + 8 * g, d0 + oBh + adv, C::IDESC2, (g != 0 || !first_slab) ? 1u : 0u);
+      tc::umma_tf32_ts(tmem_d, tmem_a + 32 + 8 * g, d0 + oBh + adv, C::IDESC, 1u);
+    }
+  }
+}
+
+template <int BN, bool RAW, bool ATM = false>
 __global__ void __launch_bounds__(RAW ? tc::THREADS_RAW : tc::THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
@@ -527,6 +566,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   using C = tc::Cfg<BN>;
   constexpr int EPI_WARPS = RAW ? tc::EPI_WARPS_RAW : tc::EPI_WARPS_SPLIT;
   constexpr int ROLE_THREADS = 64 + 32 * EPI_WARPS;   // TMA warp, MMA warp, epilogue warps; the split warps follow
+  // ATM: the A operand of the MMAs lives in tensor memory -- per ring stage 32 columns of hi (the raw words) and
+  // 32 of lo behind the two accumulator stages -- written by the split warps with tcgen05.st.  The K = 8 TF32
+  // instruction is bound by its shared-memory operand reads; A was half of them (and A_lo a shared-memory write).
+  static_assert(!ATM || (RAW && C::TMEM_COLS + 64 * C::STAGES <= 512), "A-in-TMEM needs room behind the accumulators");
+  constexpr int TMEM_ALLOC = ATM ? 512 : C::TMEM_COLS;
+  constexpr uint32_t TMEM_A0 = C::TMEM_COLS;          // first column of the A stages
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = tc::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                 // 128B swizzle needs 1024-byte alignment
@@ -562,7 +607,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32((const void*)tmem_slot)), "r"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32((const void*)tmem_slot)), "r"(TMEM_ALLOC) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc::tc_fence_before();
@@ -627,6 +672,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           if (dbg && kb == 0 && tile == (int)blockIdx.x) dbg[3] = c1;
           const int krem = p.K - kb * tc::BK;
           const int ngran = krem >= tc::BK ? 4 : (krem + 7) >> 3;   // K granules of 8 that hold data
+          if (ATM) {
+            const uint32_t ta = tmem_base + TMEM_A0 + 64u * stage;
+            switch (stage) {
+              case 0: tc_issue_slab_ts<BN, 0>(d0, tmem_d, ta, ngran, kb == 0); break;
+              case 1: tc_issue_slab_ts<BN, C::STAGE_BYTES>(d0, tmem_d, ta, ngran, kb == 0); break;
+              case 2: tc_issue_slab_ts<BN, 2 * C::STAGE_BYTES>(d0, tmem_d, ta, ngran, kb == 0); break;
+              default: tc_issue_slab_ts<BN, (C::STAGES - 1) * C::STAGE_BYTES>(d0, tmem_d, ta, ngran, kb == 0); break;
+            }
+          } else
           switch (stage) {
             case 0: tc_issue_slab<BN, 0>(d0, tmem_d, ngran, kb == 0); break;
             case 1: tc_issue_slab<BN, C::STAGE_BYTES>(d0, tmem_d, ngran, kb == 0); break;
@@ -676,6 +730,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       float4* b_lo = reinterpret_cast<float4*>(sa + 2 * tc::A_BYTES + C::B_BYTES);
       // batches of eight 16-byte chunks per thread: enough loads in flight, 32 registers
       constexpr int BATCH = 8;
+      if (ATM) {
+        // A goes to tensor memory: every thread owns one tile row (TMEM lane 32 (warp % 4) + lane), reads its
+        // 128 swizzled bytes of the raw slab and stores 32 columns of hi (the raw words: the tensor core
+        // drops the low mantissa bits itself) and 32 of lo
+        const int r = 32 * (warp & 3) + lane;
+        const uint8_t* arow = sa + r * 128;
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 x = *reinterpret_cast<const float4*>(arow + ((j ^ (r & 7)) << 4));
+          hi[4 * j + 0] = __float_as_uint(x.x); lo[4 * j + 0] = __float_as_uint(tc::lo1(x.x));
+          hi[4 * j + 1] = __float_as_uint(x.y); lo[4 * j + 1] = __float_as_uint(tc::lo1(x.y));
+          hi[4 * j + 2] = __float_as_uint(x.z); lo[4 * j + 2] = __float_as_uint(tc::lo1(x.z));
+          hi[4 * j + 3] = __float_as_uint(x.w); lo[4 * j + 3] = __float_as_uint(tc::lo1(x.w));
+        }
+        const uint32_t ta = tmem_base + TMEM_A0 + 64u * stage + ((uint32_t)(32 * (warp & 3)) << 16);
+        tc::tmem_st32(ta, hi);
+        tc::tmem_st32(ta + 32, lo);
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+      } else {
 #pragma unroll
       for (int j0 = 0; j0 < A_CH / NT; j0 += BATCH) {
         float4 x[BATCH];
@@ -683,6 +758,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         for (int j = 0; j < BATCH; ++j) x[j] = a_hi[t + (j0 + j) * NT];
 #pragma unroll
         for (int j = 0; j < BATCH; ++j) a_lo[t + (j0 + j) * NT] = tc::lo4(x[j]);
+      }
       }
       constexpr int B_IT = (B_CH + NT - 1) / NT;
 #pragma unroll
@@ -740,7 +816,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   }
   if (warp == 2) {
     tc::tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_ALLOC) : "memory");
   }
 }
 
@@ -1167,6 +1243,8 @@ static int g_tc_tma_store = 1;   // raw kernel: C through TMA stores (0: direct 
 int tc_tune_tma_store(int on) { g_tc_tma_store = on ? 1 : 0; return 0; }
 static int g_tc_exp = 0;
 int tc_tune_exp(int v) { g_tc_exp = v; return 0; }
+static int g_tc_atm = 1;   // BN = 64 raw kernel: A operand of the MMAs in tensor memory (0: in shared memory)
+int tc_tune_atm(int on) { g_tc_atm = on ? 1 : 0; return 0; }
 static int g_tc_dual = 1;  // pair independent same-shape products into one launch
 int tc_tune_dual(int on) { g_tc_dual = on; return 0; }
 static long long* g_tc_dbg = nullptr;   // developer timeline buffer (uglad_tc_debug_buffer)
@@ -1179,7 +1257,7 @@ static void fill_epi(TcEpi& e, const TcGemm& g) {
 }
 
 // g2 == nullptr: one product; otherwise two independent products of identical shape in one launch
-template <int BN, bool RAW>
+template <int BN, bool RAW, bool ATM = false>
 static int launch_tc(const TcGemm& g, const TcGemm* g2, int batch, cudaStream_t st) {
   using C = tc::Cfg<BN>;
   static bool attr_set[MAX_DEV] = {false};   // the function attribute is per device
@@ -1187,7 +1265,7 @@ static int launch_tc(const TcGemm& g, const TcGemm* g2, int batch, cudaStream_t 
   UGLAD_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= MAX_DEV) { set_error("device ordinal %d out of range", dev); return 1; }
   if (!attr_set[dev]) {
-    UGLAD_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    UGLAD_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, RAW, ATM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     RAW ? C::SMEM_RAW : C::SMEM));
     attr_set[dev] = true;
   }
@@ -1244,7 +1322,7 @@ static int launch_tc(const TcGemm& g, const TcGemm* g2, int batch, cudaStream_t 
   attr[0].val.programmaticStreamSerializationAllowed = g_tc_pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  UGLAD_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, RAW>, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], mc[0], mc[1],
+  UGLAD_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, RAW, ATM>, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], mc[0], mc[1],
                                 mcp[0], mcp[1], p));
   profile_end(st);
   UGLAD_CHECK_LAUNCH("tc_gemm_kernel");
@@ -1292,7 +1370,8 @@ static int launch_tc_any(const TcGemm& g, const TcGemm* g2, int batch, cudaStrea
     }
   }
   switch (bn) {
-    case 64: return raw ? launch_tc<64, true>(g, g2, batch, st) : launch_tc<64, false>(g, g2, batch, st);
+    case 64: return raw ? (g_tc_atm ? launch_tc<64, true, true>(g, g2, batch, st) : launch_tc<64, true>(g, g2, batch, st))
+                        : launch_tc<64, false>(g, g2, batch, st);
     case 112: return raw ? launch_tc<112, true>(g, g2, batch, st) : launch_tc<112, false>(g, g2, batch, st);
     case 128: return raw ? launch_tc<128, true>(g, g2, batch, st) : launch_tc<128, false>(g, g2, batch, st);
   }

@@ -113,6 +113,7 @@ bool tc_chain_enabled();
 int tc_tune_chain(int on);
 int tc_tune_chain_bn(int bn);
 int tc_tune_dual(int on);
+int tc_tune_atm(int on);
 int tc_tune_bn(int bn);
 int tc_tune_pdl(int on);
 int tc_tune_tma_store(int on);   // 1 (default): the raw-operand kernel writes C with TMA stores

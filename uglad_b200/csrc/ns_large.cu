@@ -183,6 +183,7 @@ int ns_tune(const char* key, int value) {
   if (!strcmp(key, "tc_raw")) return tc_tune_raw(value);
   if (!strcmp(key, "tc_tma_store")) return tc_tune_tma_store(value);
   if (!strcmp(key, "tc_exp")) return tc_tune_exp(value);
+  if (!strcmp(key, "tc_atm")) return tc_tune_atm(value);
   if (!strcmp(key, "tc_chain")) return tc_tune_chain(value);
   if (!strcmp(key, "tc_chain_bn")) return tc_tune_chain_bn(value);
   return 1;
