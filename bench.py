@@ -268,7 +268,7 @@ def shard_range(total, rank, world):
     return int(idx[0]), int(idx[-1]) + 1
 
 
-def time_gpu_workload(name, steps, warmup, rank, world, group, dev, scaling="weak", profile=False):
+def time_gpu_workload(name, steps, warmup, rank, world, group, dev, scaling="weak", profile=False, use_graph=True):
     """One workload on this rank's GPU.  `value`: covariances resident in HBM.  `e2e`: every step
     starts from the sample matrices in pinned host memory (H2D, covariance, conditioning,
     fwd + bwd + Adam, loss back to the host).  `prof`: a separate pass with CUDA-event brackets
@@ -308,7 +308,7 @@ def time_gpu_workload(name, steps, warmup, rank, world, group, dev, scaling="wea
         B = X_host.shape[0]
         S, loss_S = prepare_data.get_covariance(X_host.to(dev)), None
     torch.manual_seed(0)
-    model, opt = ug.init_uGLAD(lr=0.002, theta_init_offset=1.0, nF=3, H=3)
+    model, opt = ug.init_uGLAD(lr=0.002, theta_init_offset=1.0, nF=3, H=3, capturable=True)
     ops.reset_warm_start()
 
     def sync_all():
@@ -317,12 +317,32 @@ def time_gpu_workload(name, steps, warmup, rank, world, group, dev, scaling="wea
             dist.barrier(group=group)
             torch.cuda.synchronize(dev)
 
-    def step(Sb, lS=None):
+    def step_eager(Sb, lS=None):
         opt.zero_grad()
         _, loss = ug.forward_uGLAD(Sb, model, L=L_LAYERS, INIT_DIAG=0, loss_Sb=lS, group=grp, total_graphs=B_total)
         loss.backward()
         opt.step()
         return loss
+
+    # The epoch is replayed from CUDA graphs (ops.GraphedStep: two alternating captures, each seeded by the other's
+    # workspace); the eager path stays for the per-kernel profiling pass and as the fallback if capture fails.
+    gs, graph_note = None, None
+    if use_graph:
+        try:
+            gs = ops.GraphedStep(S, model, opt, L=L_LAYERS, INIT_DIAG=0, loss_S=loss_S, group=grp, total_graphs=B_total)
+        except Exception as exc:   # e.g. a collective that cannot be captured on this stack
+            graph_note = f"capture failed, eager launches: {type(exc).__name__}: {str(exc)[:120]}"
+            torch.cuda.synchronize(dev)
+            ops.reset_warm_start()
+    replayed = [0]
+
+    def step(Sb, lS=None):
+        if gs is None:
+            return step_eager(Sb, lS)
+        if Sb is not S:
+            gs.update_inputs(Sb, lS)
+        replayed[0] += gs.kernels_per_graph[gs.calls & 1]
+        return gs.step()[1]
 
     # e2e: every step consumes a fresh copy of the samples from pinned host memory (H2D,
     # covariance, conditioning) and returns its loss to the host.  As a data loader would, the
@@ -379,10 +399,10 @@ def time_gpu_workload(name, steps, warmup, rank, world, group, dev, scaling="wea
 
     for _ in range(warmup):
         step(S, loss_S)
-    c0 = lib.uglad_launch_count()
+    c0, r0 = lib.uglad_launch_count(), replayed[0]
     with ClockSampler(dev.index) as clk:
         ms_total = timed(lambda: step(S, loss_S), steps)
-    launches = lib.uglad_launch_count() - c0
+    launches = (lib.uglad_launch_count() - c0) + (replayed[0] - r0)   # eager launches + kernels replayed from the graphs
     # e2e: the training step runs on a high-priority stream, so that the staging of the NEXT batch (H2D,
     # covariance, conditioning on the prefetcher's ordinary-priority side stream) fills idle SM slots instead
     # of delaying the kernels on the step's critical path
@@ -397,7 +417,7 @@ def time_gpu_workload(name, steps, warmup, rank, world, group, dev, scaling="wea
     if profile:
         psteps = max(1, min(steps, 5))
         lib.uglad_profile(1, None, None)
-        ms_prof = timed(lambda: step(S, loss_S), psteps)
+        ms_prof = timed(lambda: step_eager(S, loss_S), psteps)
         prof = {"steps": psteps, "ms_per_step": ms_prof / psteps}
         for kind, kname in KERNELS:
             k_ms, k_n, k_work = ctypes.c_double(0), ctypes.c_ulonglong(0), ctypes.c_double(0)
@@ -410,7 +430,9 @@ def time_gpu_workload(name, steps, warmup, rank, world, group, dev, scaling="wea
     units = B_total * L_LAYERS * steps
     del S, loss_S
     ops.reset_warm_start()
-    return dict(value=units / ms_total * 1e3, ms_per_step=ms_total / steps, e2e_value=units / ms_e2e * 1e3,
+    del gs
+    return dict(cuda_graph=(graph_note or ("replayed" if use_graph else "off")),
+                value=units / ms_total * 1e3, ms_per_step=ms_total / steps, e2e_value=units / ms_e2e * 1e3,
                 e2e_ms_per_step=ms_e2e / steps, h2d=int(X_host.numel() * 4), d2h=4, launches=int(launches),
                 prof=prof, clocks=clk.summary(), B=B, B_total=B_total, D=D, M=M)
 
@@ -509,6 +531,7 @@ def main():
     ap.add_argument("--workload", default="multitask_d100", choices=sorted(WORKLOADS))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-extra", action="store_true", help="skip the extra per-config measurements")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay of the epoch")
     args = ap.parse_args()
     # stdout carries exactly ONE line, the JSON result: everything else that libraries print there
     # (NCCL's "NCCL version ..." banner under torchrun, for one) is sent to stderr
@@ -550,13 +573,15 @@ def main():
     wl = args.workload
     spec = WORKLOADS[wl]
     scaling = "strong" if spec.get("consensus") else args.scaling
-    r = time_gpu_workload(wl, args.steps, args.warmup, rank, world, group, dev, scaling=scaling, profile=True)
+    r = time_gpu_workload(wl, args.steps, args.warmup, rank, world, group, dev, scaling=scaling, profile=True,
+                          use_graph=not args.no_graph)
     extra = {}
 
     def extra_entry(name, x, with_cpu):
         e = {"baseline_config_index": WORKLOADS[name]["config_index"], "value": x["value"], "unit": UNIT,
              "ms_per_step": x["ms_per_step"], "e2e_value": x["e2e_value"], "e2e_ms_per_step": x["e2e_ms_per_step"],
              "h2d_bytes_per_step": x["h2d"], "graphs_total": x["B_total"], "graphs_per_gpu": x["B"],
+             "cuda_graph": x["cuda_graph"],
              "gpu_launches": x["launches"], "roofline": roofline_of(x, peaks)}
         if with_cpu and rank == 0:
             e["cpu_baseline"] = cpu_baseline_object(name)
@@ -566,16 +591,17 @@ def main():
         if world == 1:
             for name, st, wu in (("single_d100", args.steps, args.warmup), ("consensus_d200", min(args.steps, 10), 3),
                                  ("single_d1000", min(args.steps, 5), 3)):
-                x = time_gpu_workload(name, st, wu, rank, world, group, dev, scaling="strong", profile=True)
+                x = time_gpu_workload(name, st, wu, rank, world, group, dev, scaling="strong", profile=True,
+                                      use_graph=not args.no_graph)
                 extra[name] = extra_entry(name, x, with_cpu=True)
         else:
             # the literal configs[2] / configs[3]: a FIXED 256-graph batch / 32 imputations over the N GPUs
             if scaling == "weak":
                 x = time_gpu_workload("multitask_d100", args.steps, args.warmup, rank, world, group, dev,
-                                      scaling="strong", profile=False)
+                                      scaling="strong", profile=False, use_graph=not args.no_graph)
                 extra["multitask_d100_strong"] = dict(extra_entry("multitask_d100", x, with_cpu=False), scaling="strong")
             x = time_gpu_workload("consensus_d200", min(args.steps, 10), 3, rank, world, group, dev, scaling="strong",
-                                  profile=False)
+                                  profile=False, use_graph=not args.no_graph)
             extra["consensus_d200"] = dict(extra_entry("consensus_d200", x, with_cpu=False), scaling="strong")
             extra["shard_check"] = shard_check(rank, world, group, dev)
 
@@ -588,7 +614,8 @@ def main():
             "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl, "baseline_config_index": spec["config_index"], "graphs_per_gpu": B,
                        "graphs_total": r["B_total"], "D": D, "M": r["M"], "L": L_LAYERS, "H": 3,
-                       "parallelism": f"graph-sharded x{world}", "host_numa_node": numa, "l2_policy": "working set per step exceeds L2 "
+                       "parallelism": f"graph-sharded x{world}", "host_numa_node": numa, "cuda_graph": r["cuda_graph"],
+                       "l2_policy": "working set per step exceeds L2 "
                        "(saved theta / theta_k1 / eigenvectors of 15 layers: %.0f MB)" % (B * D * D * 4 * 3 * L_LAYERS / 1e6)},
             "clocks": r["clocks"],
             "e2e": {"value": r["e2e_value"], "unit": UNIT, "ms_per_step": r["e2e_ms_per_step"],

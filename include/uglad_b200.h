@@ -134,6 +134,9 @@ typedef struct uglad_peers {
   int rank;                       /* this process                                                     */
   unsigned tag;                   /* call counter, identical on all ranks                             */
   void* slots[UGLAD_MAX_PEERS];   /* device pointers (valid in THIS process) to every rank's buffer  */
+  void* tag_dev;                  /* optional device uint32 (zero-initialised, private to this rank): when set
+                                   * the counter lives there (layer 0 increments it) and `tag` is ignored, so
+                                   * that a captured CUDA graph of the call can be replayed                  */
 } uglad_peers;
 size_t uglad_peer_slots_bytes(int L);
 int uglad_glad_forward_sharded(const uglad_dims* d, const float* S, const float* params, const float* wS,

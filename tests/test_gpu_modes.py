@@ -124,3 +124,42 @@ def test_consensus_covariances_match_the_reference_pipeline():
     want = O.covariance([X[tr] for tr, _ in O.kfold_blocks(203, 5)])
     assert rel(S_K.cpu().numpy(), want) < 5e-6
     assert rel(Sb.cpu().numpy(), O.covariance(X[None])) < 5e-6
+
+
+@pytest.mark.parametrize("B,D", [(3, 20), (1, 100), (2, 200)])
+def test_graphed_epochs_equal_eager_epochs(B, D):
+    """ops.GraphedStep: the epoch (zero_grad, forward, loss, backward, Adam) captured as two alternating CUDA
+    graphs and replayed must walk the same training trajectory as eager calls -- same kernels, same
+    warm-start chain (each epoch seeded by the previous one's workspace), capturable Adam on both sides."""
+    from uglad_b200 import main as ug, ops
+    rng = np.random.default_rng(B * 100 + D)
+    X = rng.random((B, 3 * D, D))
+    S = torch.tensor(O.covariance(X), dtype=torch.float32).cuda()
+    E = 9
+
+    def fresh():
+        torch.manual_seed(5)
+        model, opt = ug.init_uGLAD(lr=0.01, capturable=True)
+        with torch.no_grad():
+            model.rho_l1[4].bias.fill_(-6.0)
+        ops.reset_warm_start()
+        return model, opt
+
+    model, opt = fresh()
+    eager = []
+    for _ in range(E):
+        opt.zero_grad()
+        th, loss = ug.forward_uGLAD(S, model, L=15)
+        loss.backward()
+        opt.step()
+        eager.append(loss.item())
+    th_e = th.detach().clone()
+    model, opt = fresh()
+    gs = ops.GraphedStep(S, model, opt, L=15)
+    n_eager = gs.eager_epochs
+    graphed = []
+    for _ in range(E - n_eager):
+        th, loss = gs.step()
+        graphed.append(loss.item())
+    assert np.allclose(graphed, eager[n_eager:], rtol=2e-6, atol=1e-6), (graphed, eager[n_eager:])
+    assert rel(th.cpu().numpy(), th_e.cpu().numpy()) < 2e-5

@@ -20,7 +20,8 @@ class UgladDims(C.Structure):
 
 
 class UgladPeers(C.Structure):
-    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("tag", C.c_uint), ("slots", C.c_void_p * 8)]
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("tag", C.c_uint), ("slots", C.c_void_p * 8),
+                ("tag_dev", C.c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol include/uglad_b200.h declares

@@ -522,6 +522,7 @@ int uglad_glad_forward_sharded(const uglad_dims* d, const float* S, const float*
   }
   PeerSlots ps;
   ps.world = peers->world; ps.rank = peers->rank; ps.tag = peers->tag;
+  ps.tag_dev = reinterpret_cast<unsigned*>(peers->tag_dev);
   for (int r = 0; r < peers->world; ++r) {
     if (!peers->slots[r]) { set_error("glad_forward_sharded: slots[%d] is NULL", r); return 1; }
     ps.slots[r] = reinterpret_cast<unsigned long long*>(peers->slots[r]);

@@ -41,11 +41,13 @@ __global__ void lambda_step_kernel(int k, const float* params, int H, float lamb
   if (k == 0) {
     x0 = lambda_init;
     x1 = 0.f;
+    if (peers.tag_dev) *peers.tag_dev += 1u;   // a new forward call (identical sequence on every rank)
   } else {
     float total = normf[k - 1];
     if (peers.world > 1) {
-      const size_t slot = ((size_t)(peers.tag & 1u) * L + (k - 1)) * UGLAD_MAX_PEERS;
-      const unsigned long long word = ((unsigned long long)peers.tag << 32) | (unsigned long long)__float_as_uint(total);
+      const unsigned tag = peers.tag_dev ? *peers.tag_dev : peers.tag;
+      const size_t slot = ((size_t)(tag & 1u) * L + (k - 1)) * UGLAD_MAX_PEERS;
+      const unsigned long long word = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(total);
       for (int r = 0; r < peers.world; ++r) {
         volatile unsigned long long* dst = peers.slots[r] + slot + peers.rank;
         *dst = word;
@@ -58,7 +60,7 @@ __global__ void lambda_step_kernel(int k, const float* params, int H, float lamb
         unsigned long long w;
         for (int spin = 0;; ++spin) {
           w = mine[r];
-          if ((unsigned)(w >> 32) == peers.tag) break;
+          if ((unsigned)(w >> 32) == tag) break;
           if ((spin & 1023) == 1023) {
             const long long now = clock64();
             if (t0 == 0) t0 = now;

@@ -171,6 +171,8 @@ struct PeerSlots {
   unsigned long long* slots[UGLAD_MAX_PEERS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int world = 1, rank = 0;
   unsigned tag = 0;
+  unsigned* tag_dev = nullptr;   // when set: the call counter lives on the device (layer 0 increments it), so that a
+                                 // captured CUDA graph of the forward can be replayed
 };
 int launch_lambda_step(int k, const float* params, int H, float lambda_init, int B_total,
                        float* normf, float* lam, float* lamfeat, cudaStream_t st, const PeerSlots* peers = nullptr,

@@ -9,10 +9,12 @@ from torch.optim import Adam, Optimizer
 from .. import ops
 
 
-def get_optimizers(model_glad: nn.Module, lr_glad: float = 0.002, use_optimizer: str = "adam") -> Optimizer:
-    """glad.py:11-36."""
+def get_optimizers(model_glad: nn.Module, lr_glad: float = 0.002, use_optimizer: str = "adam",
+                   capturable: bool = False) -> Optimizer:
+    """glad.py:11-36.  `capturable`: keep Adam's step counter on the device so that the whole epoch can be
+    captured in a CUDA graph (ops.GraphedStep)."""
     if use_optimizer == "adam":
-        return Adam(model_glad.parameters(), lr=lr_glad, betas=(0.9, 0.999), eps=1e-08)
+        return Adam(model_glad.parameters(), lr=lr_glad, betas=(0.9, 0.999), eps=1e-08, capturable=capturable)
     raise ValueError("Optimizer not found! Supported optimizers: ['adam']")
 
 

@@ -24,10 +24,10 @@ from .utils.metrics import report_metrics_all
 
 
 # ---- model ------------------------------------------------------------------------------
-def init_uGLAD(lr: float, theta_init_offset: float = 1.0, nF: int = 3, H: int = 3):
-    """main.py:233-249."""
+def init_uGLAD(lr: float, theta_init_offset: float = 1.0, nF: int = 3, H: int = 3, capturable: bool = False):
+    """main.py:233-249.  `capturable`: an optimizer that ops.GraphedStep can capture in a CUDA graph."""
     model = GladParams(theta_init_offset=theta_init_offset, nF=nF, H=H)
-    return model, glad.get_optimizers(model, lr_glad=lr)
+    return model, glad.get_optimizers(model, lr_glad=lr, capturable=capturable)
 
 
 def loss_uGLAD(theta: torch.Tensor, S: torch.Tensor, struct_theta: Optional[torch.Tensor] = None,

@@ -242,6 +242,7 @@ class PeerExchange:
                 check(lib.uglad_peer_open(bytes(every[r].cpu().tolist()), C.byref(p)), "uglad_peer_open")
                 self.slots.append(p.value)
         self.tag = 0
+        self.tag_dev = torch.zeros(1, dtype=torch.int32, device=device)   # device-side call counter (graph replay)
         dist.barrier(group=group)   # every rank has mapped every buffer before the first store
 
     @classmethod
@@ -257,6 +258,7 @@ class PeerExchange:
         p.world, p.rank, p.tag = self.world, self.rank, self.tag
         for r, v in enumerate(self.slots):
             p.slots[r] = v
+        p.tag_dev = self.tag_dev.data_ptr()
         return p
 
 
@@ -265,6 +267,24 @@ def _use_peer_exchange(S: torch.Tensor, group) -> bool:
         return False
     import torch.distributed as dist
     return dist.get_backend(group) == "nccl" and dist.get_world_size(group) <= 8
+
+
+# explicit (workspace, warm-start workspace) for the next forward: GraphedStep captures the epoch with two static
+# workspaces that seed each other instead of the allocate-and-cache scheme of eager calls
+_forced_ws = None
+
+
+class use_workspace:
+    def __init__(self, ws: torch.Tensor, warm: Optional[torch.Tensor]):
+        self.pair = (ws, warm)
+
+    def __enter__(self):
+        global _forced_ws
+        _forced_ws = self.pair
+
+    def __exit__(self, *a):
+        global _forced_ws
+        _forced_ws = None
 
 
 class GladFunction(torch.autograd.Function):
@@ -288,12 +308,19 @@ class GladFunction(torch.autograd.Function):
         n = lib.uglad_workspace_floats(C.byref(dims))
         if n == 0:
             raise _lib.UgladError(lib.uglad_last_error().decode())
-        ws = torch.empty(n, device=S.device, dtype=torch.float32)
+        forced = _forced_ws
+        if forced is not None:
+            ws, warm = forced
+            if ws.numel() < n or (warm is not None and warm.numel() < n):
+                raise _lib.UgladError("use_workspace: workspace smaller than uglad_workspace_floats")
+        else:
+            ws = torch.empty(n, device=S.device, dtype=torch.float32)
         # warm start: the previous forward's workspace for the same problem shape (normally the
         # previous epoch of the same fit) seeds the eigensolver; see uglad_glad_forward.
         wkey = (B, D, L, H, init_diag, S.device.index, lib.uglad_small_d_max(), n)
         tkey = getattr(S, "_uglad_warm_key", None) or (S.data_ptr(), S._version)
-        warm = _warm_lookup(wkey, tkey) if warm_start_enabled else None
+        if forced is None:
+            warm = _warm_lookup(wkey, tkey) if warm_start_enabled else None
         eig = _eig_of(S) if (init_diag == 0 and D <= lib.uglad_small_d_max()) else None
         wS, VtS = (eig.wS, eig.VtS) if eig is not None else (None, None)
         st = _stream(S)
@@ -315,7 +342,7 @@ class GladFunction(torch.autograd.Function):
                                                    _ptr(warm), st), "uglad_glad_layer_forward")
 
             run_sharded_layers(L, layer, ws[off:off + L], group)
-        if warm_start_enabled:
+        if warm_start_enabled and forced is None:
             _warm_store(wkey, tkey, ws)
         off = lib.uglad_workspace_offset(C.byref(dims), b"theta")
         theta = ws[off:off + B * D * D].view(B, D, D)
@@ -360,6 +387,98 @@ class GlassoLossFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         return ctx.grad * gout, None, None, None
+
+
+def workspace_floats(B, D, L, H=3, init_diag=0, B_total=None) -> int:
+    dims = make_dims(B, D, L, H, init_diag, B_total)
+    n = _lib.load().uglad_workspace_floats(C.byref(dims))
+    if n == 0:
+        raise _lib.UgladError(_lib.load().uglad_last_error().decode())
+    return int(n)
+
+
+class GraphedStep:
+    """One training epoch of the reference loop (main.py:389-414: zero_grad, unrolled GLAD forward, glasso
+    loss, backward, Adam step) captured as CUDA graphs and replayed: the ~260 kernel launches of an epoch
+    cost one graph launch, which is what bounds small batches (one graph at D = 100: ~5 us of launch and
+    dependency latency around every small kernel).  Two graphs alternate because every epoch's eigensolver
+    is seeded by the previous epoch's workspace: graph 0 works in workspace X seeded by Y, graph 1 in Y
+    seeded by X.  The inputs live in static buffers (update_inputs copies new covariances in); the
+    optimizer must be capturable (glad.get_optimizers(..., capturable=True)).  With `group` the epoch is
+    the graph-sharded one: the layers exchange their Frobenius sums through peer memory (device-side call
+    counter) and the gradient all-reduce is captured with the rest."""
+
+    def __init__(self, S, model, optimizer, L=15, INIT_DIAG=0, loss_S=None, struct_theta=None, group=None,
+                 total_graphs=None):
+        from . import main as ug
+        if not all(g.get("capturable", False) for g in optimizer.param_groups):
+            raise _lib.UgladError("GraphedStep needs a capturable optimizer: glad.get_optimizers(model, lr, capturable=True)")
+        dev = S.device
+        self.S = S.detach().clone()
+        cc = _eig_of(S)
+        self.cc = ConditionedCovariance.__new__(ConditionedCovariance)
+        self.cc.S = self.S
+        self.cc.wS = None if cc.wS is None else cc.wS.clone()
+        self.cc.VtS = None if cc.VtS is None else cc.VtS.clone()
+        self.cc.info = None
+        self.S._uglad_eig = (self.S._version, self.cc)
+        self.loss_S = None if loss_S is None else loss_S.detach().clone()
+        B, D = S.shape[0], S.shape[1]
+        n = workspace_floats(B, D, L, model.H, INIT_DIAG, total_graphs)
+        self.ws = [torch.empty(n, device=dev, dtype=torch.float32) for _ in range(2)]
+        self.model, self.opt = model, optimizer
+        self.calls = 0
+
+        def epoch(i, warm):
+            with use_workspace(self.ws[i], warm):
+                optimizer.zero_grad(set_to_none=True)
+                theta, loss = ug.forward_uGLAD(self.S, model, L=L, INIT_DIAG=INIT_DIAG, loss_Sb=self.loss_S,
+                                               struct_theta=struct_theta, group=group, total_graphs=total_graphs)
+                loss.backward()
+                optimizer.step()
+            return theta.detach(), loss.detach()
+
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        self.eager_out = []
+        with torch.cuda.stream(side):   # eager epochs: fill both workspaces (cold, then warm) and the optimizer state
+            self.eager_out.append(epoch(0, None))
+            self.eager_out.append(epoch(1, self.ws[0]))
+            self.eager_out.append(epoch(0, self.ws[1]))
+            self.eager_out.append(epoch(1, self.ws[0]))
+        self.eager_out = [(None, l.clone()) for _, l in self.eager_out]
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.eager_epochs = 4
+        self.graphs, self.out, self.kernels_per_graph = [], [], []
+        lib = _lib.load()
+        pool = None
+        for i in range(2):
+            g = torch.cuda.CUDAGraph()
+            c0 = lib.uglad_launch_count()
+            with torch.cuda.graph(g, pool=pool):
+                self.out.append(epoch(i, self.ws[1 - i]))
+            self.kernels_per_graph.append(int(lib.uglad_launch_count() - c0))   # library kernels replayed per epoch
+            pool = g.pool()
+            self.graphs.append(g)
+
+    def update_inputs(self, S, loss_S=None):
+        """New covariances of the same shape (and their eigendecomposition, get_covariance attaches it)."""
+        self.S.copy_(S)
+        cc = _eig_of(S)
+        if self.cc.wS is not None:
+            self.cc.wS.copy_(cc.wS)
+            self.cc.VtS.copy_(cc.VtS)
+        if loss_S is not None:
+            self.loss_S.copy_(loss_S)
+
+    def step(self):
+        """Replay one epoch; returns (theta_pred, loss) as static tensors (overwritten two steps later)."""
+        i = self.calls & 1
+        self.calls += 1
+        self.graphs[i].replay()
+        return self.out[i]
 
 
 def z_update(X, S, theta_prev, flat_params, H=3):
