@@ -254,7 +254,7 @@ def run_reference(args, wl, rank, world):
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
-KERNELS = ((0, "eig_jacobi_small_kernel"), (1, "tc_gemm_kernel"))
+KERNELS = ((0, "eig_jacobi_oe_kernel"), (1, "tc_gemm_kernel"))   # kind 0: the eigensolver launches (warm: eig_cluster.cu)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, read from the committed `ncu --set full`
 # captures under profiles/ (the file is named in the roofline object): keyed by (kernel, graphs, D)
 NCU_TRAFFIC = {
@@ -416,6 +416,8 @@ def time_gpu_workload(name, steps, warmup, rank, world, group, dev, scaling="wea
     prof = None
     if profile:
         psteps = max(1, min(steps, 5))
+        for _ in range(2):   # the eager path keeps its own warm-start chain: seed it before the brackets go on
+            step_eager(S, loss_S)
         lib.uglad_profile(1, None, None)
         ms_prof = timed(lambda: step_eager(S, loss_S), psteps)
         prof = {"steps": psteps, "ms_per_step": ms_prof / psteps}
@@ -443,7 +445,7 @@ def roofline_of(r, peaks):
     prof = r["prof"]
     if not prof:
         return None
-    eig, tcg = prof["eig_jacobi_small_kernel"], prof["tc_gemm_kernel"]
+    eig, tcg = prof["eig_jacobi_oe_kernel"], prof["tc_gemm_kernel"]
     step_ms = prof["ms_per_step"] * prof["steps"]
     if tcg["launches"] and tcg["ms"] >= eig["ms"]:
         key = "bf16_tflops_sustained"
@@ -475,7 +477,7 @@ def roofline_of(r, peaks):
     hbm_peak = peaks.get("hbm_gbs") or 6650.0
     hbm_ach = eig["work"] / (eig["ms"] * 1e-3) / 1e9
     traffic = NCU_TRAFFIC.get(("eig", r["B"], r["D"]), (None, None))
-    return {"bound": "fp32", "kernel": "eig_jacobi_small_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+    return {"bound": "fp32", "kernel": "eig_jacobi_oe_kernel (warm layer solves; eig_jacobi_small_kernel: the loss solve)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak, "traffic": traffic[0], "traffic_source": traffic[1],
             "peak_source": f"148 SMs x 128 FP32 lanes x 2 x {sm_mhz:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz)",
             "avg_launch_ms": eig["ms"] / eig["launches"], "launches_per_step": eig["launches"] / prof["steps"],

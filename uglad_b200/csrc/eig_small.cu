@@ -225,6 +225,9 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
   __shared__ unsigned s_rot, s_dots;      // profiling (a.work != nullptr): applied rotations, column-pair dot products
 
   const int b = blockIdx.x;
+  // retry pass behind the cluster kernel (eig_cluster.cu): only the graphs it flagged (info[0] >= 1000: the warm
+  // start was not positive definite) are solved, from scratch with the guaranteed shift
+  if (a.retry_only && !(a.info[(size_t)b * 4] >= 1000.f)) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nthreads = blockDim.x, nwarps = nthreads >> 5;
   const int nch = ld >> 2;
@@ -251,7 +254,7 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
 
   float sigma = 0.f, trace = 0.f, wsum = 0.f;
   long long t_start = clock64(), t_sweeps0 = 0, t_sweeps1 = 0;
-  for (int attempt = 0; attempt < 2; ++attempt) {
+  for (int attempt = a.retry_only ? 1 : 0; attempt < 2; ++attempt) {
     if (attempt == 0 && a.U0 != nullptr) {
       // pre-multiplied warm start: U_0 = (A + sigma I) V_prev was formed by a tcgen05 GEMM; nothing else to set up
       const float* U0b = a.U0 + (size_t)b * D * a.ldu;
@@ -749,6 +752,7 @@ __global__ void __launch_bounds__(eig_max_threads(LP, CH), 1) eig_jacobi_small_k
   }
   if (a.info && tid == 0) {
     float* o = a.info + (size_t)b * 4;
+    if (a.retry_only) sweeps += 1000;
     o[0] = (float)sweeps;
     o[1] = sigma;
     o[2] = trace;
@@ -821,7 +825,9 @@ static int g_tune_keepg = -1;  // -1 = auto (keep G when two buffers fit); 0 / 1
 static int g_tune_timing = 0;
 static int g_tune_mma = 1;     // 1 = warm-start product and Rayleigh quotients on the mma.sync tensor path
 static int g_tune_pad = 1;     // 1 = pad shared-memory columns to LP*CH*4 floats when it fits
+int eig_small_timing() { return g_tune_timing; }
 int eig_small_tune(const char* key, int value) {
+  if (!eig_cluster_tune(key, value)) return 0;
   if (!strcmp(key, "eig_lp")) { g_tune_lp = value; return 0; }
   if (!strcmp(key, "eig_keepg")) { g_tune_keepg = value; return 0; }
   if (!strcmp(key, "eig_tol_1e7")) { g_tune_tol_1e7 = value; return 0; }
@@ -840,9 +846,9 @@ static int launch_cfg(const EigArgs& a, int B, size_t smem, cudaStream_t st) {
   if (threads < a.D) threads = ((a.D + 31) / 32) * 32;  // the power iteration wants a thread per row
   UGLAD_CUDA(cudaFuncSetAttribute(eig_jacobi_small_kernel<LP, CH, PAD>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  profile_begin(st, 0, (double)B * (4.0 * a.D * a.D + 3.0 * a.D) * 4.0);
+  if (!a.retry_only) profile_begin(st, 0, (double)B * (4.0 * a.D * a.D + 3.0 * a.D) * 4.0);   // (the retry pass is not a solve)
   eig_jacobi_small_kernel<LP, CH, PAD><<<B, threads, smem, st>>>(a);
-  profile_end(st);
+  if (!a.retry_only) profile_end(st);
   UGLAD_CHECK_LAUNCH("eig_jacobi_small_kernel");
   return 0;
 }
@@ -856,6 +862,21 @@ int launch_eig_small(const EigArgs& a_in, int B, cudaStream_t st) {
   if (a.D > UGLAD_SMALL_D_MAX) {
     set_error("eig_small: D=%d exceeds the shared-memory solver limit %d", a.D, UGLAD_SMALL_D_MAX);
     return 1;
+  }
+  if (a.U0 != nullptr && a.info != nullptr && !a.retry_only) {
+    // small batches: the graph's column pairs spread over a cluster of CTAs (eig_cluster.cu), then a retry pass of
+    // this kernel for the graphs whose warm start failed the positive-definiteness check (normally none: the
+    // CTAs of the pass exit at once)
+    const int nc = eig_cluster_size(B, a.D);
+    if (nc > 0) {
+      const int rc = launch_eig_cluster(a, B, nc, st);
+      if (rc == 1) return 1;
+      if (rc == 0) {
+        EigArgs r = a_in;
+        r.retry_only = 1;
+        return launch_eig_small(r, B, st);
+      }
+    }
   }
   int nch = a.ld / 4;
   // lanes per column pair: narrow groups replicate the rotation scalar math less (the kernel

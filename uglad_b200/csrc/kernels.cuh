@@ -31,6 +31,7 @@ struct EigArgs {
   const float* pre_sigma = nullptr;
   const float* pre_trace = nullptr;
   int ldu = 0;
+  int retry_only = 0;            // set by the launcher: solve only the graphs the cluster kernel flagged (info[0] >= 1000)
   int keepG = 0;                 // set by the launcher: second shared-memory buffer holds A + sigma I
   int D = 0, ld = 0, build = 0, shift_mode = 1, tail = TAIL_PLAIN, exact_sqrt = 0;
   int max_sweeps = 40;
@@ -45,6 +46,11 @@ struct EigArgs {
 };
 int launch_eig_small(const EigArgs& a, int B, cudaStream_t st);
 int eig_small_tune(const char* key, int value);
+int eig_small_timing();
+// warm solves over a cluster of nc CTAs per graph (eig_cluster.cu); 0 ok, 1 error, 2 no configuration for the shape
+int launch_eig_cluster(const EigArgs& a, int B, int nc, cudaStream_t st);
+int eig_cluster_size(int B, int D);   // CTAs per graph the cluster kernel would use for this batch (0: one-CTA kernel)
+int eig_cluster_tune(const char* key, int value);
 int launch_eig(const EigArgs& a, int B, cudaStream_t st);  // dispatch on D
 // optional CUDA-event bracket around the eigensolver launches (bench.py's roofline leg)
 void profile_begin(cudaStream_t st, int kind, double work);  // kind 0 eigensolver (bytes), 1 tcgen05 GEMM (flops)
