@@ -95,6 +95,12 @@ int uglad_condition_covariance_x(float* S, const float* X, const float* mean, in
  * Newton-Schulz iteration as dense products (tcgen05 3xTF32) and logdet / inverses come from a
  * blocked Cholesky.  uglad_eigh itself is only available up to this size.                  */
 int uglad_small_d_max(void);
+/* 1 when a batch of B graphs of size D takes the eigensolver path, 0 for the Newton-Schulz chain: D <=
+ * uglad_small_d_max(), and -- while a batch is small enough for every graph's warm solves to spread over a
+ * resident cluster of 4 CTAs (csrc/eig_cluster.cu) -- D <= 200 with D % 4 == 0 (configs[3]: 32 x D = 200).
+ * It concerns the layers (uglad_glad_*): conditioning, theta_0 and the glasso loss switch at
+ * uglad_small_d_max() alone (wS / VtS are NULL above it).                                              */
+int uglad_eig_path(int B, int D);
 
 /* (2)+(3) the unrolled model.  The workspace holds everything the backward needs
  * (theta_k1, theta_pred, eigenvectors, eigenvalues per layer) plus scratch.              */

@@ -10,10 +10,12 @@ from uglad_b200.utils import prepare_data
 lib = _lib.load(); dev = torch.device("cuda:0")
 args = [int(x) for x in sys.argv[1:]]
 cases = list(zip(args[0::2], args[1::2])) or [(1, 100), (32, 100), (3, 20), (2, 164), (64, 100), (256, 100)]
+if os.environ.get("SMALL_D_MAX"): ops.tune("small_d_max", int(os.environ["SMALL_D_MAX"]))
+NCS = [int(x) for x in os.environ.get("NCS", "0,1,2,4").split(",")]
 for B, D in cases:
     S = prepare_data.get_covariance(torch.from_numpy(bench.synth(B, D, 1000, 1234)).to(dev))
     base = None
-    for nc in (0, 1, 2, 4):
+    for nc in NCS:
         ops.tune("eig_cluster", nc)
         ops.tune("eig_timing", 0)
         ops.reset_warm_start()

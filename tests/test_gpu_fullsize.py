@@ -315,7 +315,7 @@ def test_peer_exchange_forward_reproduces_the_whole_batch(D, small_d_max):
         ops.tune("small_d_max", 166)
 
 
-@pytest.mark.parametrize("B,D", [(2, 256), (4, 200), (1, 333)])
+@pytest.mark.parametrize("B,D", [(2, 256), (4, 204), (1, 333)])
 def test_persistent_chain_launch_is_bit_identical_to_separate_launches(B, D):
     """uglad_tune("tc_chain", 1): the ten Newton-Schulz iterations of a layer (forward: 19 stages, backward:
     30 stages incl. the in-kernel antisymmetrisation) as ONE persistent launch with grid barriers.  Same

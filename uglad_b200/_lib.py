@@ -42,6 +42,7 @@ SIGNATURES = {
     "uglad_condition_scratch_floats": (_Z, [_I, _I]),
     "uglad_condition_covariance_x": (_I, [_P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
     "uglad_small_d_max": (_I, []),
+    "uglad_eig_path": (_I, [_I, _I]),
     "uglad_workspace_floats": (_Z, [_DP]),
     "uglad_workspace_offset": (_Z, [_DP, C.c_char_p]),
     "uglad_glad_init_forward": (_I, [_DP, _P, _P, _P, _P, _P, _P]),

@@ -57,6 +57,17 @@ void profile_end(cudaStream_t st) {
 // the tcgen05 Newton-Schulz chain is faster (measured crossover D ~ 155-180, profiles/r01_path_sweep.log)
 static int g_small_d_max = 166;
 static inline int small_d_max() { return g_small_d_max; }
+// Small batches: up to D = 200 the warm solves spread over clusters of 4 CTAs (eig_cluster.cu) beat the chain
+// (32 x D = 200, configs[3]: 14.4 -> 9.0 ms per epoch); the extension applies only while the cluster kernel does
+// (every cluster resident at once) and the base threshold is at its default (the tests lower it to force the chain).
+// It concerns the LAYERS only (theta update forward + backward): conditioning, theta_0 and the loss keep the
+// Cholesky forms above small_d_max (no eigendecomposition of S is kept there).
+static int g_small_d_cluster_max = 200;
+static inline bool eig_path(int B, int D) {
+  if (D <= g_small_d_max) return true;
+  return g_small_d_max >= 166 && D <= g_small_d_cluster_max && D <= UGLAD_SMALL_D_MAX && D % 4 == 0 &&
+         eig_cluster_size(B, D) == 4;
+}
 
 static inline size_t al4(size_t x) { return (x + 3) & ~(size_t)3; }
 
@@ -75,7 +86,7 @@ static Ws ws_layout(const uglad_dims* d) {
   w.n2 = B * D * D;
   w.nblk = (size_t)elem_blocks_per_graph(d->D) * B;
   w.NPR = rho_param_count(d->H);
-  w.large = d->D > small_d_max();
+  w.large = !eig_path(d->B, d->D);
   size_t o = 0;
   auto take = [&](size_t n) { size_t r = o; o += al4(n); return r; };
   w.theta = take((L + 1) * w.n2);
@@ -108,7 +119,7 @@ static Ws ws_layout(const uglad_dims* d) {
   w.t0_part = take(w.nblk);
   w.eig_scratch = take(eig_scratch_floats(d->B, d->D));
   w.ns_scratch = take(w.large ? ns_scratch_floats(d->B, d->D) : 0);
-  w.chol_scratch = take(w.large ? chol_scratch_floats(d->B, d->D) : 0);
+  w.chol_scratch = take(d->D > small_d_max() ? chol_scratch_floats(d->B, d->D) : 0);   // theta_0 by Cholesky (also on the cluster-extended eigensolver path)
   w.total = o;
   return w;
 }
@@ -118,7 +129,7 @@ static int check_dims(const uglad_dims* d) {
   if (d->B <= 0 || d->D <= 0 || d->L <= 0) { set_error("bad dims B=%d D=%d L=%d", d->B, d->D, d->L); return 1; }
   if (d->H <= 0 || d->H > UGLAD_MAX_H) { set_error("H=%d outside [1,%d]", d->H, UGLAD_MAX_H); return 1; }
   if (d->B_total < d->B) { set_error("B_total=%d < B=%d", d->B_total, d->B); return 1; }
-  if (d->D > small_d_max() && d->exact_sqrt) {
+  if (!eig_path(d->B, d->D) && d->exact_sqrt) {
     set_error("exact_sqrt is only available on the eigensolver path (D <= %d)", small_d_max());
     return 1;
   }
@@ -380,6 +391,7 @@ int uglad_condition_covariance(float* S, int B, int D, float offset, float* wS, 
 }
 
 int uglad_small_d_max(void) { return small_d_max(); }
+int uglad_eig_path(int B, int D) { return eig_path(B, D) ? 1 : 0; }
 
 size_t uglad_workspace_floats(const uglad_dims* d) {
   if (check_dims(d)) return 0;
@@ -411,7 +423,7 @@ int uglad_glad_init_forward(const uglad_dims* d, const float* S, const float* pa
   UGLAD_CUDA(cudaMemsetAsync(ws + w.counter, 0, 4 * sizeof(float), st));
   if (w.large && ns_scratch_init(ws + w.ns_scratch, d->B, d->D, st)) return 1;
   if (d->init_diag == 1) return launch_theta_init_diag(S, params, d->B, d->D, ws + w.theta, st);
-  if (w.large) {  // theta_0 = (S + t I)^-1 by Cholesky
+  if (d->D > small_d_max()) {  // theta_0 = (S + t I)^-1 by Cholesky (the eigendecomposition of S is only kept up to small_d_max)
     float* cs = ws + w.chol_scratch;
     if (launch_copy_shift(S, (long long)d->D * d->D, d->B, d->D, 0.f, params, ws + w.T1, st)) return 1;
     if (chol_factor(ws + w.T1, d->B, d->D, 0.f, nullptr, nullptr, cs, st)) return 1;
@@ -788,6 +800,7 @@ int uglad_tune(const char* key, int value) {
   if (!key) return 1;
   if (!strcmp(key, "eig_raw")) { g_eig_raw = value ? 1 : 0; return 0; }
   if (!strcmp(key, "eig_pre")) { g_eig_pre = value ? 1 : 0; return 0; }
+  if (!strcmp(key, "small_d_cluster_max")) { g_small_d_cluster_max = value; return 0; }
   if (!strcmp(key, "small_d_max")) {
     if (value < 0 || value > UGLAD_SMALL_D_MAX) { set_error("small_d_max must lie in [0, %d]", UGLAD_SMALL_D_MAX); return 1; }
     g_small_d_max = value;

@@ -557,7 +557,7 @@ __global__ void __launch_bounds__(oe_max_threads(LP, CH), MINB) eig_jacobi_oe_ke
     if (lane == 0) a.w[(size_t)b * D + col] = nrm - sigma;
   }
   if (a.work != nullptr) {
-    if (lane == 0 && rot_count) atomicAdd(&s_rot, rot_count);
+    if (gl == 0 && rot_count) atomicAdd(&s_rot, rot_count);
     __syncthreads();
     if (tid == 0) {
       // dot products: the sweeps + every check pass (counted once per graph), rotations of this CTA's groups

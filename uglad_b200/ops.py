@@ -317,7 +317,7 @@ class GladFunction(torch.autograd.Function):
             ws = torch.empty(n, device=S.device, dtype=torch.float32)
         # warm start: the previous forward's workspace for the same problem shape (normally the
         # previous epoch of the same fit) seeds the eigensolver; see uglad_glad_forward.
-        wkey = (B, D, L, H, init_diag, S.device.index, lib.uglad_small_d_max(), n)
+        wkey = (B, D, L, H, init_diag, S.device.index, lib.uglad_eig_path(B, D), n)
         tkey = getattr(S, "_uglad_warm_key", None) or (S.data_ptr(), S._version)
         if forced is None:
             warm = _warm_lookup(wkey, tkey) if warm_start_enabled else None
