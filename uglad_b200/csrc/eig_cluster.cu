@@ -157,7 +157,7 @@ __device__ __forceinline__ float fold(unsigned long long g01, unsigned long long
   return (g0 + g1) + (g2 + g3);
 }
 
-constexpr int MAXFIX = 64;
+constexpr int MAXFIX = 192;
 constexpr int MAXNC = 4;
 
 }  // namespace oe
@@ -180,6 +180,8 @@ __global__ void __launch_bounds__(oe_max_threads(LP, CH), MINB) eig_jacobi_oe_ke
   __shared__ unsigned s_flag, s_nfix, s_rot;
   __shared__ unsigned s_fix[MAXFIX];
   __shared__ unsigned s_fixs[MAXFIX];
+  __shared__ unsigned s_owner[256];   // fix-up rounds: lowest pending list index per column (D <= 200)
+  __shared__ unsigned s_left;
   __shared__ unsigned x_cnt[2][MAXNC], x_flag[2][MAXNC];   // exchanged between the CTAs, double-buffered by exchange parity
   __shared__ unsigned x_fix[2][MAXNC][MAXFIX];
   __shared__ __align__(8) unsigned long long s_mbar[2];   // boundary columns arriving from rank - 1 / rank + 1
@@ -263,6 +265,7 @@ __global__ void __launch_bounds__(oe_max_threads(LP, CH), MINB) eig_jacobi_oe_ke
   const uint32_t tx_bytes = (uint32_t)(LP * CH * 16 + 4);
   unsigned ph_lo = 0, ph_hi = 0;
   int sweeps = 0, xpar = 0;
+  int st_fix = 0, st_over = 0, st_maxlist = 0, st_rounds = 0;   // developer knob eig_timing = 2: fix-up rotations, full-sweep reasons, longest list
   unsigned rot_count = 0;
   bool converged = false;
   long long t_sweep_cycles = 0, t_check_cycles = 0, t_fix_cycles = 0, t_load_end = 0;
@@ -472,7 +475,9 @@ __global__ void __launch_bounds__(oe_max_threads(LP, CH), MINB) eig_jacobi_oe_ke
       const int xp = xpar;
       xpar ^= 1;
       if (worstb == 0u) { converged = true; break; }
-      if (overflow || total > (unsigned)MAXFIX || fixrounds >= 2) break;   // full sweep
+      st_maxlist = max(st_maxlist, (int)total);
+      if (overflow || total > (unsigned)MAXFIX || fixrounds >= 2) { st_over += (fixrounds >= 2 && !overflow && total <= (unsigned)MAXFIX) ? 100 : 1; break; }   // full sweep
+      st_fix += (int)total;
       // merged list in ascending (p, q) order: the result must not depend on who found what first
       for (unsigned ei = tid; ei < total; ei += nthreads) {
         unsigned mine = 0, acc = 0;
@@ -487,11 +492,31 @@ __global__ void __launch_bounds__(oe_max_threads(LP, CH), MINB) eig_jacobi_oe_ke
         s_fixs[rk] = mine;
       }
       __syncthreads();
-      // one listed pair after the other (they may share columns), by the first warp of EVERY CTA on its own copy
-      if (warp == 0) {
-        for (unsigned f = 0; f < total; ++f) {
-          const unsigned pq = s_fixs[f];
+      // Fix-up rotations in PARALLEL rounds with the result of the sequential pass: every pending pair claims its two
+      // columns with its list index (atomicMin); a pair that holds both rotates now, the others wait.  Two pairs that
+      // share a column therefore run in list order, disjoint rotations commute exactly -- same numbers as one
+      // pair after the other, in (longest chain through a shared column) rounds instead of `total`.  Every CTA of
+      // the cluster does this on its own copy (identical lists, identical arithmetic).
+      for (;;) {
+        for (int i = tid; i < D; i += nthreads) s_owner[i] = 0xffffffffu;
+        if (tid == 0) s_left = 0u;
+        __syncthreads();
+        for (unsigned e = tid; e < total; e += nthreads) {
+          const unsigned pq = s_fixs[e];
+          if (!(pq & 0x80000000u)) {
+            atomicMin(&s_owner[pq >> 16], e);
+            atomicMin(&s_owner[pq & 0xffffu], e);
+          }
+        }
+        __syncthreads();
+        for (unsigned e = lg; e < total; e += lgroups) {
+          const unsigned pq = s_fixs[e];
+          if (pq & 0x80000000u) continue;
           const int p = (int)(pq >> 16), q = (int)(pq & 0xffffu);
+          if (s_owner[p] != e || s_owner[q] != e) {
+            if (gl == 0) s_left = 1u;
+            continue;
+          }
           float* up = F + (size_t)p * ld + 4 * gl;
           float* uq = F + (size_t)q * ld + 4 * gl;
           float4 pa[CH], pb[CH];
@@ -502,28 +527,30 @@ __global__ void __launch_bounds__(oe_max_threads(LP, CH), MINB) eig_jacobi_oe_ke
             pb[c] = *reinterpret_cast<const float4*>(uq + 4 * LP * c);
             dot4acc(pa[c], pb[c], g01, g23);
           }
-          const float ga = group_sum<LP>(fold(g01, g23));
+          const float ga = group_sum_masked<LP>(fold(g01, g23), gmask);
           const float al = nrm2[p], be = nrm2[q];
           Rot r;
-          const bool doit = rotation(al, be, ga, tol2, r);
-          __syncwarp();
-          if (doit && lane < LP) {
+          if (rotation(al, be, ga, tol2, r)) {
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
               rotate4(r, pa[c], pb[c]);
               *reinterpret_cast<float4*>(up + 4 * LP * c) = pa[c];
               *reinterpret_cast<float4*>(uq + 4 * LP * c) = pb[c];
             }
-            if (lane == 0) {
+            if (gl == 0) {
               nrm2[p] = fmaxf(fmaf(-r.t, ga, al), 0.f);
               nrm2[q] = fmaf(r.t, ga, be);
               ++rot_count;
             }
           }
-          __syncwarp();
+          if (gl == 0) s_fixs[e] = pq | 0x80000000u;
         }
+        __syncthreads();
+        const bool more = s_left != 0u;
+        ++st_rounds;
+        __syncthreads();
+        if (!more) break;
       }
-      __syncthreads();
       t_fix_cycles += clock64() - t_c1;
       // every listed |cos| < 1e-3: the untouched pairs moved by theta * tol at most, no re-check (eig_small.cu)
       if (worst2 < 1e-6f) { converged = true; break; }
@@ -571,6 +598,11 @@ __global__ void __launch_bounds__(oe_max_threads(LP, CH), MINB) eig_jacobi_oe_ke
     o[1] = sigma;
     o[2] = trace;
     o[3] = wsum - (float)D * sigma;
+    if (a.timing == 2 && pd) {
+      o[1] = (float)st_fix;
+      o[2] = (float)(st_over + 1000 * st_rounds);   // + 1000 x parallel fix-up rounds
+      o[3] = (float)st_maxlist;
+    }
     if (a.timing == 3 && pd) {
       o[1] = (float)(t_load_end - t_start);
       o[2] = (float)t_check_cycles;
@@ -597,7 +629,7 @@ static int launch_oe_cfg(const EigArgs& a, int B, int nc, int gpc, int threads, 
   int dev = 0;
   UGLAD_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 16 || !attr_set[dev]) {
-    UGLAD_CUDA(cudaFuncSetAttribute(eig_jacobi_oe_kernel<LP, CH, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    UGLAD_CUDA(cudaFuncSetAttribute(eig_jacobi_oe_kernel<LP, CH, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
     if (dev >= 0 && dev < 16) attr_set[dev] = true;
   }
   cudaLaunchConfig_t cfg = {};
@@ -654,7 +686,7 @@ int launch_eig_cluster(const EigArgs& a_in, int B, int nc, cudaStream_t st) {
   a.ld = lp * chT * 4 + 4;
   const int Dp = (D + 3) & ~3;
   const size_t smem = ((size_t)a.ld * D + 2 * Dp + 32) * sizeof(float);
-  if (smem > 220 * 1024) return 2;
+  if (smem > 216 * 1024) return 2;
   a.timing = eig_small_timing();
   a.work = profile_eig_counters();
 #define UGLAD_OE_CASE(LP_, CH_)                                                                    \
