@@ -258,7 +258,8 @@ KERNELS = ((0, "eig_jacobi_oe_kernel"), (1, "tc_gemm_kernel"))   # kind 0: the e
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, read from the committed `ncu --set full`
 # captures under profiles/ (the file is named in the roofline object): keyed by (kernel, graphs, D)
 NCU_TRAFFIC = {
-    ("eig", 256, 100): (30.8e6, "profiles/r01_ncu_full_eig_multitask_d100_v6.txt"),
+    ("eig", 256, 100): (10.35e6, "profiles/r02_ncu_full_eig_oe_multitask_d100.txt"),
+    ("eig", 1, 100): (0.0965e6, "profiles/r02_ncu_full_eig_oe_single_d100.txt"),
     ("tc", 1, 1000): (10.7e6, "profiles/r01_ncu_full_tc_gemm_d1000_v4.txt"),
 }
 
