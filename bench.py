@@ -97,14 +97,52 @@ def kfold_train(M, K):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """SM clocks / throttle reasons sampled while the timed region runs: NVML in a thread (one query per 50 ms;
+    eight ranks each forking nvidia-smi loops starved one another and returned no samples), nvidia-smi as the
+    fallback when the NVML binding is missing."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.sm, self.mx, self.reasons, self.stop, self.th, self.nvml = [], [], set(), False, None, None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        self.nvml = pynvml
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            return pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        except Exception:
+            return pynvml.nvmlDeviceGetHandleByIndex(self.index)
+
+    def _poll(self, h):
+        n = self.nvml
+        while not self.stop:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+                self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)))
+                mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                for name, bit in self.REASONS:
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
 
     def __enter__(self):
+        try:
+            h = self._nvml_handle()
+            self.th = threading.Thread(target=self._poll, args=(h,), daemon=True)
+            self.th.start()
+            return self
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -120,14 +158,18 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *a):
-        if self.proc is not None:
+        if self.nvml is not None:
+            time.sleep(0.06)
+            self.stop = True
+            self.th.join(timeout=2)
+        elif self.proc is not None:
             time.sleep(0.15)
             self.proc.terminate()
             self.th.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        sm, mx, reasons = list(self.sm), list(self.mx), set(self.reasons)
+        names = [n for n, _ in self.REASONS]
         for r in self.rows:
             try:
                 sm.append(float(r[0]))

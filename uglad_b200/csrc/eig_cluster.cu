@@ -23,6 +23,7 @@
 // A start that turns out not to be positive definite (sum of column norms != trace + D sigma) is
 // flagged in info[0] (+1000); the launcher then runs the one-CTA kernel in retry mode for those graphs.
 #include <string.h>
+#include <type_traits>
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -145,6 +146,26 @@ __device__ __forceinline__ void rotate4(const Rot& r, float4& a, float4& b) {
   upk2(na01, a.x, a.y); upk2(na23, a.z, a.w);
   upk2(nb01, b.x, b.y); upk2(nb23, b.z, b.w);
 }
+// The sweep's rotation scalars, branch-free and with three MUFU operations on the dependent chain (the step loop is
+// one long dependent chain: its instruction count is its time): with h = sqrt(d^2 + g2^2), d = be - al, g2 = 2 ga,
+//   cos^2 = (1 + |d| / h) / 2,  sin = sign(d) g2 / (2 h cos),  tau = sin / (1 + cos),  tan = sin / cos
+// (the same angle as rotation(): tan 2 theta = g2 / d, smaller root).  MUFU accuracy (2^-22) is enough here: in the
+// small-angle-accurate update form the error of the applied rotation scales with the rotation itself, and the
+// fix-up pass polishes with rotation().  `rot` false leaves sn = tau = t = 0: the update is then the identity.
+__device__ __forceinline__ void rotation_fast(float al, float be, float ga, float tol2, bool valid, Rot& r, bool& rot) {
+  const float d = be - al, g2 = ga + ga;
+  rot = valid && (ga * ga > tol2 * (al * be));
+  const float rh = fast_rsqrt(fmaf(d, d, g2 * g2));
+  const float c2 = fmaf(0.5f * fabsf(d), rh, 0.5f);
+  const float rcs = fast_rsqrt(c2);
+  const float cs = c2 * rcs;
+  float sn = (0.5f * g2) * (rh * rcs);
+  sn = (d < 0.f) ? -sn : sn;
+  const float tau = sn * fast_rcp(1.f + cs);
+  r.sn = rot ? sn : 0.f;
+  r.tau = rot ? tau : 0.f;
+  r.t = rot ? sn * rcs : 0.f;
+}
 __device__ __forceinline__ float dot4acc(const float4& a, const float4& b, unsigned long long& g01, unsigned long long& g23) {
   g01 = ffma2(pk2(a.x, a.y), pk2(b.x, b.y), g01);
   g23 = ffma2(pk2(a.z, a.w), pk2(b.z, b.w), g23);
@@ -174,8 +195,8 @@ __global__ void __launch_bounds__(oe_max_threads(LP, CH), MINB) eig_jacobi_oe_ke
   const int D = a.D, ld = a.ld;
   const int Dp = (D + 3) & ~3;
   float* F = smem;                           // [D][ld] column at every position (this CTA's copy)
-  float* nrm2 = F + (size_t)ld * D;          // [Dp] squared column norms by position
-  float* wv = nrm2 + Dp;                     // [Dp] final column norms
+  float* nrm2 = F + (size_t)ld * (D + 1);    // [Dp + 4] squared column norms by position (+ the scratch column's, at [D])
+  float* wv = nrm2 + Dp + 4;                 // [Dp] final column norms; F[D] is a scratch column (the idle group's mirror)
   float* red = wv + Dp;                      // [32]
   __shared__ unsigned s_flag, s_nfix, s_rot;
   __shared__ unsigned s_fix[MAXFIX];
@@ -292,62 +313,79 @@ __global__ void __launch_bounds__(oe_max_threads(LP, CH), MINB) eig_jacobi_oe_ke
       if (act && gl == 0) nrm2[2 * g] = ne;
     }
     __syncthreads();
-    // ---- D steps of the odd-even ordering -----------------------------------------------------
-    for (int s = 0; s < D; ++s) {
-      const int odd = s & 1;
-      const int e = 2 * gc + 2 * odd;
-      const bool valid = act && e < D;
-      const int ec = valid ? e : 0;
-      const float* ue = F + (size_t)ec * ld + 4 * gl;
-      if (edge_lo && !odd && s > 0) {   // the column the lower neighbour pushed in the previous step
-        mbar_wait(mb_lo, ph_lo & 1u);
-        ++ph_lo;
-        if (gl == 0) mbar_arm(mb_lo, tx_bytes);
-      }
-      if (edge_hi && odd) {
-        mbar_wait(mb_hi, ph_hi & 1u);
-        ++ph_hi;
-        if (gl == 0) mbar_arm(mb_hi, tx_bytes);
-      }
-      float4 bv[CH];
-      unsigned long long g01 = 0ull, g23 = 0ull;
-#pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        bv[c] = *reinterpret_cast<const float4*>(ue + 4 * LP * c);
-        dot4acc(av[c], bv[c], g01, g23);
-      }
-      const float ga = group_sum<LP>(fold(g01, g23));
-      const float al = na, be = nrm2[ec];
-      Rot r;
-      float nal = al, nbe = be;
-      if (valid && rotation(al, be, ga, tol2, r)) {
-#pragma unroll
-        for (int c = 0; c < CH; ++c) rotate4(r, av[c], bv[c]);
-        nal = fmaxf(fmaf(-r.t, ga, al), 0.f);
-        nbe = fmaf(r.t, ga, be);
-        if (gl == 0) ++rot_count;
-      }
-      if (valid) {
-        // swap: the rotated register column goes to the even position (in the CTA of its next reader),
-        // the rotated partner stays in registers
-        if (odd ? edge_hi : edge_lo) {
-          const uint32_t dstF = (odd ? F_odd : F_even) + (uint32_t)(((size_t)ec * ld + 4 * gl) * sizeof(float));
-          const uint32_t dstN = (odd ? N_odd : N_even) + (uint32_t)(ec * sizeof(float));
-          const uint32_t mb = odd ? mb_peer_hi : mb_peer_lo;
-#pragma unroll
-          for (int c = 0; c < CH; ++c) st_async_f4(dstF + (uint32_t)(16 * LP * c), av[c], mb);
-          if (gl == 0) st_async_f1(dstN, nal, mb);
-        } else {   // the reader is a group of this CTA: plain shared-memory stores
-          float* ud = F + (size_t)ec * ld + 4 * gl;
-#pragma unroll
-          for (int c = 0; c < CH; ++c) *reinterpret_cast<float4*>(ud + 4 * LP * c) = av[c];
-          if (gl == 0) nrm2[ec] = nal;
+    // ---- D steps of the odd-even ordering: D / 2 (even, odd) pairs.  The loop body is a dependent chain whose
+    // instruction count IS its time, so: everything that depends only on the step's parity is formed once out
+    // here; the two register arrays trade roles instead of being copied (a step loads the partner into `oth`,
+    // rotates, stores the rotated `cur` and continues with `oth` as its own column); and the one group that has no
+    // partner in the odd steps (the last one: position D - 1 waits there) pairs with a MIRROR of its own column in
+    // the scratch slot F[D] with the rotation switched off, so that the role swap stays unconditional.
+    {
+      const bool is_last = act && (g == ng - 1);
+      const bool valid_o = act && !is_last;
+      float* const ue_e = F + (size_t)(2 * gc) * ld + 4 * gl;                                       // even step: position 2g
+      float* const ue_o = F + (size_t)(valid_o ? 2 * gc + 2 : (is_last ? D : 0)) * ld + 4 * gl;     // odd step : position 2g + 2
+      float* const ne_e = nrm2 + 2 * gc;
+      float* const ne_o = nrm2 + (valid_o ? 2 * gc + 2 : (is_last ? D : 0));
+      const uint32_t dstF_e = F_even + (uint32_t)(((size_t)(2 * gc) * ld + 4 * gl) * sizeof(float));
+      const uint32_t dstF_o = F_odd + (uint32_t)(((size_t)(valid_o ? 2 * gc + 2 : 0) * ld + 4 * gl) * sizeof(float));
+      const uint32_t dstN_e = N_even + (uint32_t)(2 * gc * sizeof(float));
+      const uint32_t dstN_o = N_odd + (uint32_t)((valid_o ? 2 * gc + 2 : 0) * sizeof(float));
+      auto step = [&](auto oddc, bool first, float4 (&cur)[CH], float4 (&oth)[CH]) {
+        constexpr bool ODD = decltype(oddc)::value;
+        const bool valid = ODD ? valid_o : act;
+        const bool edge = ODD ? edge_hi : edge_lo;
+        float* const ue = ODD ? ue_o : ue_e;
+        float* const ne = ODD ? ne_o : ne_e;
+        if (edge && !(first && !ODD)) {   // the column the neighbour CTA pushed in the previous step
+          const uint32_t mb = ODD ? mb_hi : mb_lo;
+          unsigned& ph = ODD ? ph_hi : ph_lo;
+          mbar_wait(mb, ph & 1u);
+          ++ph;
+          if (gl == 0) mbar_arm(mb, tx_bytes);
         }
+        unsigned long long g01 = 0ull, g23 = 0ull;
 #pragma unroll
-        for (int c = 0; c < CH; ++c) av[c] = bv[c];
-        na = nbe;
+        for (int c = 0; c < CH; ++c) {
+          oth[c] = *reinterpret_cast<const float4*>(ue + 4 * LP * c);
+          dot4acc(cur[c], oth[c], g01, g23);
+        }
+        const float be = *ne;
+        const float ga = group_sum<LP>(fold(g01, g23));
+        const float al = na;
+        Rot r;
+        bool rot;
+        rotation_fast(al, be, ga, tol2, valid, r, rot);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) rotate4(r, cur[c], oth[c]);
+        const float nal = fmaxf(fmaf(-r.t, ga, al), 0.f);
+        na = fmaf(r.t, ga, be);        // the rotated partner is this group's column from here on
+        rot_count += rot ? 1u : 0u;    // (every lane counts; lane 0 of the group reports)
+        if (valid) {
+          // swap: the rotated former own column goes to the even position (in the CTA of its next reader)
+          if (edge) {
+            const uint32_t dstF = ODD ? dstF_o : dstF_e, dstN = ODD ? dstN_o : dstN_e;
+            const uint32_t mb = ODD ? mb_peer_hi : mb_peer_lo;
+#pragma unroll
+            for (int c = 0; c < CH; ++c) st_async_f4(dstF + (uint32_t)(16 * LP * c), cur[c], mb);
+            if (gl == 0) st_async_f1(dstN, nal, mb);
+          } else {   // the reader is a group of this CTA: plain shared-memory stores
+#pragma unroll
+            for (int c = 0; c < CH; ++c) *reinterpret_cast<float4*>(ue + 4 * LP * c) = cur[c];
+            if (gl == 0) *ne = nal;
+          }
+        }
+        if (!ODD && is_last) {   // mirror of the new own column for the partner-less odd step
+#pragma unroll
+          for (int c = 0; c < CH; ++c) *reinterpret_cast<float4*>(ue_o + 4 * LP * c) = oth[c];
+          if (gl == 0) *ne_o = na;
+        }
+        __syncthreads();
+      };
+      float4 bv[CH];
+      for (int s2 = 0; s2 < (D >> 1); ++s2) {
+        step(std::false_type{}, s2 == 0, av, bv);
+        step(std::true_type{}, false, bv, av);
       }
-      __syncthreads();
     }
     if (edge_lo) {   // the last odd step's push from below (the final column at this CTA's first even position)
       mbar_wait(mb_lo, ph_lo & 1u);
@@ -685,7 +723,7 @@ int launch_eig_cluster(const EigArgs& a_in, int B, int nc, cudaStream_t st) {
   if (threads > oe_max_threads(lp, chT)) return 2;
   a.ld = lp * chT * 4 + 4;
   const int Dp = (D + 3) & ~3;
-  const size_t smem = ((size_t)a.ld * D + 2 * Dp + 32) * sizeof(float);
+  const size_t smem = ((size_t)a.ld * (D + 1) + 2 * Dp + 4 + 32) * sizeof(float);
   if (smem > 216 * 1024) return 2;
   a.timing = eig_small_timing();
   a.work = profile_eig_counters();
