@@ -188,8 +188,10 @@ constexpr int oe_max_threads(int, int) { return 512; }   // 128 registers: the c
 // ld = LP * CH * 4 + 4 floats per column (rows beyond D are zero): every lane owns CH float4 chunks of a
 // column, no predicates in the chunk loops; +4 keeps consecutive columns 4 banks apart.
 // MINB = 2: the one-CTA-per-graph form for full batches (64 registers, two CTAs per SM)
-template <int LP, int CH, int MINB>
-__global__ void __launch_bounds__(oe_max_threads(LP, CH), MINB) eig_jacobi_oe_kernel(EigArgs a, int nc, int gpc) {
+// MAXT = 448 with MINB = 2: 72 registers (with 64 the step loop re-forms its pointers from special registers and
+// constants at the top of every step, on the dependent chain)
+template <int LP, int CH, int MINB, int MAXT = 512>
+__global__ void __launch_bounds__(MAXT, MINB) eig_jacobi_oe_kernel(EigArgs a, int nc, int gpc) {
   using namespace oe;
   extern __shared__ __align__(16) float smem[];
   const int D = a.D, ld = a.ld;
@@ -209,7 +211,9 @@ __global__ void __launch_bounds__(oe_max_threads(LP, CH), MINB) eig_jacobi_oe_ke
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nthreads = blockDim.x, nwarps = nthreads >> 5;
-  const uint32_t rank = (nc > 1) ? cluster_rank() : 0u;
+  constexpr bool CL = (MINB == 1);   // the cluster forms; MINB = 2 is launched with one CTA per graph only
+  if (!CL) nc = 1;
+  const uint32_t rank = (CL && nc > 1) ? cluster_rank() : 0u;
   const int b = blockIdx.x / nc;
   const int ng = D >> 1;                     // lane groups of the graph (D is even on this path)
   const int lg = tid / LP, gl = tid % LP, lgroups = nthreads / LP;
@@ -221,7 +225,7 @@ __global__ void __launch_bounds__(oe_max_threads(LP, CH), MINB) eig_jacobi_oe_ke
   const long long t_start = clock64();
 
   auto block_barrier = [&]() {
-    if (nc > 1) { __syncwarp(); cluster_arrive(); cluster_wait(); }
+    if (CL && nc > 1) { __syncwarp(); cluster_arrive(); cluster_wait(); }
     else __syncthreads();
   };
 
@@ -245,7 +249,7 @@ __global__ void __launch_bounds__(oe_max_threads(LP, CH), MINB) eig_jacobi_oe_ke
     }
     if (tid == 0) {
       s_flag = 0u; s_nfix = 0u; s_rot = 0u;
-      if (nc > 1) {
+      if (CL && nc > 1) {
         mbar_init(smem_u32(&s_mbar[0]), 1u);
         mbar_init(smem_u32(&s_mbar[1]), 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -262,8 +266,8 @@ __global__ void __launch_bounds__(oe_max_threads(LP, CH), MINB) eig_jacobi_oe_ke
   uint32_t Fr[MAXNC], Nr[MAXNC];
 #pragma unroll
   for (int r = 0; r < MAXNC; ++r) {
-    Fr[r] = (nc > 1 && r < nc) ? map_rank(F_u32, (uint32_t)r) : F_u32;
-    Nr[r] = (nc > 1 && r < nc) ? map_rank(N_u32, (uint32_t)r) : N_u32;
+    Fr[r] = (CL && nc > 1 && r < nc) ? map_rank(F_u32, (uint32_t)r) : F_u32;
+    Nr[r] = (CL && nc > 1 && r < nc) ? map_rank(N_u32, (uint32_t)r) : N_u32;
   }
   // destination CTA of this group's step output: the group that reads the even position next
   //   even step: position 2g is read by group g-1 in the odd step (group 0 keeps it)
@@ -278,8 +282,8 @@ __global__ void __launch_bounds__(oe_max_threads(LP, CH), MINB) eig_jacobi_oe_ke
 
   // the two groups at the ends of this CTA's range trade one column per step with the neighbour CTAs
   const int last_lg = min(gpc, ng - g0) - 1;
-  const bool edge_lo = nc > 1 && act && lg == 0 && rank > 0;             // even steps: reads from / pushes to rank - 1
-  const bool edge_hi = nc > 1 && act && lg == last_lg && g + 1 < ng;     // odd steps : reads from / pushes to rank + 1
+  const bool edge_lo = CL && nc > 1 && act && lg == 0 && rank > 0;             // even steps: reads from / pushes to rank - 1
+  const bool edge_hi = CL && nc > 1 && act && lg == last_lg && g + 1 < ng;     // odd steps : reads from / pushes to rank + 1
   const uint32_t mb_lo = smem_u32(&s_mbar[0]), mb_hi = smem_u32(&s_mbar[1]);
   const uint32_t mb_peer_lo = edge_lo ? map_rank(mb_hi, rank - 1) : 0u;  // my downward push lands in rank-1's "from above" barrier
   const uint32_t mb_peer_hi = edge_hi ? map_rank(mb_lo, rank + 1) : 0u;
@@ -408,7 +412,7 @@ __global__ void __launch_bounds__(oe_max_threads(LP, CH), MINB) eig_jacobi_oe_ke
       if (gl == 0) nrm2[2 * g + 1] = na;
 #pragma unroll
       for (int r = 0; r < MAXNC; ++r) {
-        if (r < nc && r != (int)rank) {
+        if (CL && r < nc && r != (int)rank) {
           const uint32_t off_o = (uint32_t)(((size_t)(2 * g + 1) * ld + 4 * gl) * sizeof(float));
           const uint32_t off_e = (uint32_t)(((size_t)(2 * g) * ld + 4 * gl) * sizeof(float));
 #pragma unroll
@@ -485,7 +489,7 @@ __global__ void __launch_bounds__(oe_max_threads(LP, CH), MINB) eig_jacobi_oe_ke
         const unsigned cnt = s_nfix, flg = s_flag;
         for (int i = tid; i < nc * (MAXFIX + 2); i += nthreads) {
           const int r = i / (MAXFIX + 2), j = i - r * (MAXFIX + 2);
-          if (nc > 1) {
+          if (CL && nc > 1) {
             if (j == 0) st_cluster_u1(map_rank(smem_u32(&x_cnt[xpar][rank]), (uint32_t)r), cnt);
             else if (j == 1) st_cluster_u1(map_rank(smem_u32(&x_flag[xpar][rank]), (uint32_t)r), flg);
             else if ((unsigned)(j - 2) < min(cnt, (unsigned)MAXFIX))
@@ -652,7 +656,7 @@ __global__ void __launch_bounds__(oe_max_threads(LP, CH), MINB) eig_jacobi_oe_ke
       o[3] = (float)(clock64() - t_tail0);
     }
   }
-  if (nc > 1) { __syncwarp(); cluster_arrive(); cluster_wait(); }   // no CTA leaves while a peer may still push into its memory
+  if (CL && nc > 1) { __syncwarp(); cluster_arrive(); cluster_wait(); }   // no CTA leaves while a peer may still push into its memory
 }
 
 static int g_tune_cluster = -1;   // -1 auto; 0 off (one-CTA kernel only); 1 / 2 / 4: CTAs per graph of the odd-even kernel
@@ -661,13 +665,13 @@ int eig_cluster_tune(const char* key, int value) {
   return 1;
 }
 
-template <int LP, int CH, int MINB>
+template <int LP, int CH, int MINB, int MAXT = 512>
 static int launch_oe_cfg(const EigArgs& a, int B, int nc, int gpc, int threads, size_t smem, cudaStream_t st) {
   static bool attr_set[16] = {false};
   int dev = 0;
   UGLAD_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 16 || !attr_set[dev]) {
-    UGLAD_CUDA(cudaFuncSetAttribute(eig_jacobi_oe_kernel<LP, CH, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+    UGLAD_CUDA(cudaFuncSetAttribute(eig_jacobi_oe_kernel<LP, CH, MINB, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
     if (dev >= 0 && dev < 16) attr_set[dev] = true;
   }
   cudaLaunchConfig_t cfg = {};
@@ -683,7 +687,7 @@ static int launch_oe_cfg(const EigArgs& a, int B, int nc, int gpc, int threads, 
   cfg.attrs = attr;
   cfg.numAttrs = (nc > 1) ? 1 : 0;
   profile_begin(st, 0, (double)B * (4.0 * a.D * a.D + 3.0 * a.D) * 4.0);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, eig_jacobi_oe_kernel<LP, CH, MINB>, a, nc, gpc);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, eig_jacobi_oe_kernel<LP, CH, MINB, MAXT>, a, nc, gpc);
   profile_end(st);
   if (e != cudaSuccess) {
     set_error("eig_jacobi_oe_kernel: launch failed: %s", cudaGetErrorString(e));
@@ -729,7 +733,8 @@ int launch_eig_cluster(const EigArgs& a_in, int B, int nc, cudaStream_t st) {
   a.work = profile_eig_counters();
 #define UGLAD_OE_CASE(LP_, CH_)                                                                    \
   if (lp == LP_ && chT == CH_)                                                                    \
-    return nc == 1 ? launch_oe_cfg<LP_, CH_, 2>(a, B, nc, gpc, threads, smem, st)                 \
+    return nc == 1 ? (threads <= 448 ? launch_oe_cfg<LP_, CH_, 2, 448>(a, B, nc, gpc, threads, smem, st)    \
+                                     : launch_oe_cfg<LP_, CH_, 2>(a, B, nc, gpc, threads, smem, st))        \
                    : launch_oe_cfg<LP_, CH_, 1>(a, B, nc, gpc, threads, smem, st)
   UGLAD_OE_CASE(8, 1); UGLAD_OE_CASE(8, 2); UGLAD_OE_CASE(8, 4);
   UGLAD_OE_CASE(16, 1); UGLAD_OE_CASE(16, 2); UGLAD_OE_CASE(16, 4);
