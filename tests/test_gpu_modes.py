@@ -163,3 +163,39 @@ def test_graphed_epochs_equal_eager_epochs(B, D):
         graphed.append(loss.item())
     assert np.allclose(graphed, eager[n_eager:], rtol=2e-6, atol=1e-6), (graphed, eager[n_eager:])
     assert rel(th.cpu().numpy(), th_e.cpu().numpy()) < 2e-5
+
+
+def test_fit_loop_replays_epochs_and_keeps_the_nan_stop():
+    """main._fit_loop replays its epochs from CUDA graphs (lazy ops.GraphedStep: four eager epochs, then captures):
+    the direct mode's fit must equal the eager fit (UGLAD_EAGER_FIT=1), and the NaN stop of main.py:405-409 must
+    still leave the parameters of the epoch BEFORE the NaN loss (the replayed update is taken back)."""
+    import os
+    from uglad_b200 import main as ug, ops
+    rng = np.random.default_rng(3)
+    X = rng.random((1, 60, 20))
+    out = {}
+    for eager in ("1", "0"):
+        os.environ["UGLAD_EAGER_FIT"] = eager
+        try:
+            torch.manual_seed(4)
+            ops.reset_warm_start()
+            th, _, model = ug.run_uGLAD_direct(X, EPOCHS=14, lr=0.01, L=15, VERBOSE=False)
+            out[eager] = (th.detach().cpu().numpy(), np.array(model.loss_values_))
+        finally:
+            os.environ.pop("UGLAD_EAGER_FIT", None)
+    assert rel(out["0"][0], out["1"][0]) < 2e-5
+    assert np.allclose(out["0"][1], out["1"][1], rtol=2e-6, atol=1e-6)
+    # NaN stop on a replayed epoch: a NaN covariance makes the loss NaN
+    S = torch.tensor(O.covariance(X), dtype=torch.float32).cuda()
+    torch.manual_seed(4)
+    model, opt = ug.init_uGLAD(lr=0.01, capturable=True)
+    gs = ops.GraphedStep(S, model, opt, L=15, lazy=True, nan_guard=True)
+    for _ in range(6):
+        _, loss, stopped = gs.step_guarded(True)
+        assert not stopped
+    before = [p.detach().clone() for p in model.parameters()]
+    gs.S.fill_(float("nan"))   # the graphs' static covariance: <S, theta> and with it the loss is NaN from here on
+    _, loss, stopped = gs.step_guarded(True)
+    assert stopped and bool(torch.isnan(loss))
+    for p, q in zip(model.parameters(), before):
+        assert torch.equal(p.detach(), q)

@@ -9,6 +9,7 @@ the MAP-estimate helpers of the reference are outside this path and are not prov
 from __future__ import annotations
 
 import copy
+import os
 import sys
 from time import time
 from typing import Optional
@@ -62,7 +63,27 @@ def _fit_loop(Sb, model, optimizer, EPOCHS, L, INIT_DIAG, VERBOSE, loss_Sb=None,
     every = max(int(EPOCHS / 10), 1)
     predTheta, losses = None, []
     total = ops.global_graph_count(Sb.shape[0], Sb.device, group) if group is not None else None
+    # The epochs replay from CUDA graphs (ops.GraphedStep: four eager epochs, then two alternating captures) when the
+    # fit is long enough to pay for the capture and the optimizer is capturable; same trajectory as eager epochs.
+    gs = None
+    if (Sb.is_cuda and EPOCHS >= 8 and os.environ.get("UGLAD_EAGER_FIT", "0") != "1"
+            and all(g.get("capturable", False) for g in optimizer.param_groups)):
+        gs = ops.GraphedStep(Sb, model, optimizer, L=L, INIT_DIAG=INIT_DIAG, loss_S=loss_Sb, struct_theta=struct_theta,
+                             group=group, total_graphs=total, lazy=True, nan_guard=stop_on_nan)
     for e in range(EPOCHS):
+        if gs is not None:
+            # (sharded fits never use the NaN stop: only the direct mode does, main.py:405-409)
+            predTheta, loss, stopped = gs.step_guarded(stop_on_nan and group is None)
+            shown = loss.detach().clone()
+            if stopped:
+                print(f"Warning: NaN loss encountered at epoch {e}. Try updating the parameters and train.")
+                break
+            if VERBOSE and not e % every:
+                if group is not None:
+                    shown = ops.allreduce_sum(shown.reshape(1), group)[0]
+                print(f"{tag}epoch:{e}/{EPOCHS} loss:{shown.item()}")
+            losses.append(shown)
+            continue
         optimizer.zero_grad()
         predTheta, loss = forward_uGLAD(Sb, model, L=L, INIT_DIAG=INIT_DIAG, loss_Sb=loss_Sb,
                                         struct_theta=struct_theta, group=group, total_graphs=total)
@@ -79,6 +100,8 @@ def _fit_loop(Sb, model, optimizer, EPOCHS, L, INIT_DIAG, VERBOSE, loss_Sb=None,
             print(f"{tag}epoch:{e}/{EPOCHS} loss:{shown.item()}")
         optimizer.step()
         losses.append(shown)
+    if gs is not None and predTheta is not None:
+        predTheta = predTheta.clone()   # the replayed epochs write their theta into static buffers
     return predTheta, losses
 
 
@@ -100,7 +123,7 @@ def run_uGLAD_direct(Xb, trueTheta=None, eval_offset=0.1, EPOCHS=250, lr=0.002, 
     Sb = prepare_data.get_covariance(Xb, offset=eval_offset)
     if trueTheta is not None:
         trueTheta = prepare_data.convert_to_torch(trueTheta, req_grad=False)
-    model_glad, optimizer_glad = init_uGLAD(lr=lr, theta_init_offset=1.0, nF=3, H=3)
+    model_glad, optimizer_glad = init_uGLAD(lr=lr, theta_init_offset=1.0, nF=3, H=3, capturable=Sb.is_cuda)
     predTheta, losses = _fit_loop(Sb, model_glad, optimizer_glad, EPOCHS, L, INIT_DIAG, VERBOSE,
                                   struct_theta=trueTheta, stop_on_nan=True)
     compare_theta = None
@@ -233,7 +256,7 @@ def run_uGLAD_missing(Xb, trueTheta=None, eval_offset=0.1, EPOCHS=250, lr=0.002,
     S_K, Sb = consensus_covariances(prepare_data.convert_to_torch(Xb[0]), K_batch, eval_offset, group)
     if trueTheta is not None:
         trueTheta = prepare_data.convert_to_torch(trueTheta, req_grad=False)
-    model_glad, optimizer_glad = init_uGLAD(lr=lr, theta_init_offset=1.0, nF=3, H=3)
+    model_glad, optimizer_glad = init_uGLAD(lr=lr, theta_init_offset=1.0, nF=3, H=3, capturable=S_K.is_cuda)
     if group is not None:
         _share_model(model_glad, group)
     predTheta, _ = _fit_loop(S_K, model_glad, optimizer_glad, EPOCHS, L, INIT_DIAG, VERBOSE, loss_Sb=Sb, group=group)
@@ -254,7 +277,7 @@ def run_uGLAD_multitask(Xb, trueTheta=None, eval_offset=0.1, EPOCHS=250, lr=0.00
     Sb = prepare_data.get_covariance(Xb, offset=eval_offset)
     if trueTheta is not None:
         trueTheta = prepare_data.convert_to_torch(trueTheta, req_grad=False)
-    model_glad, optimizer_glad = init_uGLAD(lr=lr, theta_init_offset=1.0, nF=3, H=3)
+    model_glad, optimizer_glad = init_uGLAD(lr=lr, theta_init_offset=1.0, nF=3, H=3, capturable=Sb.is_cuda)
     if group is not None:
         _share_model(model_glad, group)
     predTheta, _ = _fit_loop(Sb, model_glad, optimizer_glad, EPOCHS, L, INIT_DIAG, VERBOSE, group=group)

@@ -409,7 +409,11 @@ class GraphedStep:
     counter) and the gradient all-reduce is captured with the rest."""
 
     def __init__(self, S, model, optimizer, L=15, INIT_DIAG=0, loss_S=None, struct_theta=None, group=None,
-                 total_graphs=None):
+                 total_graphs=None, lazy=False, nan_guard=False):
+        """lazy: run nothing here -- the first four step() calls are the eager epochs, the fifth captures (a fit loop
+        simply calls step() EPOCHS times; if the capture fails the epochs stay eager).  nan_guard: the NaN stop of
+        the reference's direct mode (main.py:405-409: break BEFORE the update): every epoch starts by copying the
+        parameters aside, so that step_guarded() can take a replayed update back."""
         from . import main as ug
         if not all(g.get("capturable", False) for g in optimizer.param_groups):
             raise _lib.UgladError("GraphedStep needs a capturable optimizer: glad.get_optimizers(model, lr, capturable=True)")
@@ -428,40 +432,93 @@ class GraphedStep:
         self.ws = [torch.empty(n, device=dev, dtype=torch.float32) for _ in range(2)]
         self.model, self.opt = model, optimizer
         self.calls = 0
+        self.dev = dev
+        params = [p for p in model.parameters()]
+        self.params = params
+        self.backup = [torch.empty_like(p) for p in params] if nan_guard else None
 
-        def epoch(i, warm):
+        def epoch(i, warm, guard=False):
             with use_workspace(self.ws[i], warm):
+                if self.backup is not None:
+                    with torch.no_grad():
+                        torch._foreach_copy_(self.backup, params)
                 optimizer.zero_grad(set_to_none=True)
                 theta, loss = ug.forward_uGLAD(self.S, model, L=L, INIT_DIAG=INIT_DIAG, loss_Sb=self.loss_S,
                                                struct_theta=struct_theta, group=group, total_graphs=total_graphs)
+                if guard and bool(torch.isnan(loss.detach())):
+                    return theta.detach(), loss.detach(), True   # no update (main.py:405-409)
                 loss.backward()
                 optimizer.step()
-            return theta.detach(), loss.detach()
+            return theta.detach(), loss.detach(), False
 
+        self._epoch = epoch
+        self.eager_epochs = 4
+        self.graphs, self.out, self.kernels_per_graph = None, [], []
+        self.capture_error = None
+        self._capture_tried = False
+        self.eager_out = []
+        if lazy:
+            return
         cur = torch.cuda.current_stream(dev)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(cur)
-        self.eager_out = []
         with torch.cuda.stream(side):   # eager epochs: fill both workspaces (cold, then warm) and the optimizer state
             self.eager_out.append(epoch(0, None))
             self.eager_out.append(epoch(1, self.ws[0]))
             self.eager_out.append(epoch(0, self.ws[1]))
             self.eager_out.append(epoch(1, self.ws[0]))
-        self.eager_out = [(None, l.clone()) for _, l in self.eager_out]
+        self.eager_out = [(None, o[1].clone()) for o in self.eager_out]
         cur.wait_stream(side)
-        torch.cuda.synchronize(dev)
-        self.eager_epochs = 4
-        self.graphs, self.out, self.kernels_per_graph = [], [], []
+        self._capture(strict=True)
+
+    def _capture(self, strict=False):
+        """Two alternating captures of the epoch; on failure (strict=False) the epochs simply stay eager."""
+        self._capture_tried = True
+        torch.cuda.synchronize(self.dev)
         lib = _lib.load()
+        graphs, out, kpg = [], [], []
         pool = None
-        for i in range(2):
-            g = torch.cuda.CUDAGraph()
-            c0 = lib.uglad_launch_count()
-            with torch.cuda.graph(g, pool=pool):
-                self.out.append(epoch(i, self.ws[1 - i]))
-            self.kernels_per_graph.append(int(lib.uglad_launch_count() - c0))   # library kernels replayed per epoch
-            pool = g.pool()
-            self.graphs.append(g)
+        try:
+            for i in range(2):
+                g = torch.cuda.CUDAGraph()
+                c0 = lib.uglad_launch_count()
+                with torch.cuda.graph(g, pool=pool):
+                    o = self._epoch(i, self.ws[1 - i])
+                out.append((o[0], o[1]))
+                kpg.append(int(lib.uglad_launch_count() - c0))   # library kernels replayed per epoch
+                pool = g.pool()
+                graphs.append(g)
+        except Exception as exc:
+            if strict:
+                raise
+            self.capture_error = f"{type(exc).__name__}: {str(exc)[:160]}"
+            torch.cuda.synchronize(self.dev)
+            return
+        self.graphs, self.out, self.kernels_per_graph = graphs, out, kpg
+        if self.calls >= self.eager_epochs:
+            self.calls -= self.eager_epochs   # replays are indexed from graph 0 (= the epoch after four eager ones)
+
+    def step_guarded(self, guard=False):
+        """One epoch: (theta_pred, loss, stopped).  Eager for the first four calls of a lazy instance, replayed after the
+        capture.  guard: stop on a NaN loss without applying the update (needs nan_guard=True for replayed epochs)."""
+        if self.graphs is None and not self._capture_tried and self.calls >= self.eager_epochs:
+            self._capture()
+        i = self.calls & 1
+        if self.graphs is not None:
+            self.calls += 1
+            self.graphs[i].replay()
+            theta, loss = self.out[i]
+            if guard and bool(torch.isnan(loss)):
+                if self.backup is None:
+                    raise _lib.UgladError("step_guarded(guard=True) on replayed epochs needs GraphedStep(nan_guard=True)")
+                with torch.no_grad():
+                    torch._foreach_copy_(self.params, self.backup)
+                return theta, loss, True
+            return theta, loss, False
+        warm = None if self.calls == 0 else self.ws[1 - i]
+        theta, loss, stopped = self._epoch(i, warm, guard)
+        self.calls += 1
+        return theta, loss, stopped
 
     def update_inputs(self, S, loss_S=None):
         """New covariances of the same shape (and their eigendecomposition, get_covariance attaches it)."""
@@ -474,11 +531,9 @@ class GraphedStep:
             self.loss_S.copy_(loss_S)
 
     def step(self):
-        """Replay one epoch; returns (theta_pred, loss) as static tensors (overwritten two steps later)."""
-        i = self.calls & 1
-        self.calls += 1
-        self.graphs[i].replay()
-        return self.out[i]
+        """One epoch; returns (theta_pred, loss) -- static tensors when replayed (overwritten two steps later)."""
+        theta, loss, _ = self.step_guarded(False)
+        return theta, loss
 
 
 def z_update(X, S, theta_prev, flat_params, H=3):
