@@ -621,3 +621,24 @@ def test_warm_started_conditioning_gives_the_same_covariance(dev):
     assert rel(warm.cpu().numpy(), O.covariance(X1, offset=0.1)) < 1e-5
     w_c, w_w = cold._uglad_eig[1].wS.cpu().numpy(), warm._uglad_eig[1].wS.cpu().numpy()
     assert np.abs(np.sort(w_c, 1) - np.sort(w_w, 1)).max() < 1e-5
+
+
+def test_soft_threshold_propagates_nan_like_torch(dev):
+    """glad_params.py:81 is sign(X) * max(0, |X| - rho) with torch.max / torch.sign, which propagate NaN; the
+    reference's NaN stop (main.py:405-409) depends on a diverged fit turning the loss NaN."""
+    from uglad_b200 import ops
+    rng = np.random.default_rng(9)
+    D = 12
+    X = torch.tensor(rng.standard_normal((1, D, D)), dtype=torch.float32)
+    X[0, 3, 4] = float("nan")
+    S = torch.tensor(rng.standard_normal((1, D, D)), dtype=torch.float32)
+    T = torch.tensor(rng.standard_normal((1, D, D)), dtype=torch.float32)
+    P = O.init_params(2)
+    flat = torch.cat([P[k].detach().reshape(-1) for k in O.PARAM_KEYS])
+    Z, _ = ops.z_update(X.to(dev), S.to(dev), T.to(dev), flat.to(dev), H=3)
+    Z = Z.cpu().numpy()
+    assert np.isnan(Z[0, 3, 4]) and np.isfinite(np.delete(Z.reshape(-1), 3 * D + 4)).all()
+    want = O.eta_threshold(P, X, S, T).detach().numpy()   # the oracle's torch.sign * torch.max form
+    assert np.isnan(want[0, 3, 4])
+    mask = ~np.isnan(want)
+    assert np.allclose(Z[mask], want[mask], rtol=1e-5, atol=1e-6)

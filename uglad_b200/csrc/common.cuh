@@ -177,10 +177,12 @@ struct RhoMLP {
   }
 };
 
-// soft threshold  sign(x) * max(0, |x| - rho)   (glad_params.py:77)
+// soft threshold  sign(x) * max(0, |x| - rho)   (glad_params.py:81), with torch's NaN behaviour: torch.max and torch.sign
+// both propagate NaN (fmaxf would launder it into 0 and a diverged fit would sail past the reference's NaN stop)
 __device__ __forceinline__ float soft_threshold(float x, float rho) {
-  const float m = fmaxf(fabsf(x) - rho, 0.f);
-  return (x > 0.f) ? m : ((x < 0.f) ? -m : 0.f);
+  const float d = fabsf(x) - rho;
+  const float m = (d > 0.f) ? d : ((d != d) ? d : 0.f);
+  return (x > 0.f) ? m : ((x < 0.f) ? -m : x * m);
 }
 
 }  // namespace uglad
