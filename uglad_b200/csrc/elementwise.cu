@@ -737,7 +737,6 @@ __global__ void __launch_bounds__(EW_THREADS) finalize_grads_kernel(
     const float* sgb_part, const float* t0_part, const float* lam, const float* lamfeat,
     float* grad_params) {
   __shared__ double redd[32];
-  __shared__ double s_gl[256];
   const ParamLayout pl = param_layout(H);
   const int NPR = pl.lW1 - pl.rW1;
   const int blk = blockIdx.x;
@@ -753,34 +752,56 @@ __global__ void __launch_bounds__(EW_THREADS) finalize_grads_kernel(
     s = block_sum_d(s, redd);
     if (threadIdx.x == 0) grad_params[pl.t0] = (float)(-s);
   } else {
-    for (int k = 0; k < L; ++k) {
-      double s = 0.0;
-      for (int r = threadIdx.x; r < nblk; r += EW_THREADS)
-        s += 4.0 * (double)trh_part[(size_t)k * nblk + r] + (double)sgb_part[(size_t)k * nblk + r];
-      s = block_sum_d(s, redd);
-      if (threadIdx.x == 0) {
-        const double l = lam[k];
-        s_gl[k & 255] = -s / (l * l);
-      }
-      __syncthreads();
-      // chain through lambda_f at (x0, x1) = lamfeat[k]; one thread, 4H+1 outputs
-      if (threadIdx.x == 0) {
-        const double gl = s_gl[k & 255];
-        const double x0 = lamfeat[2 * k], x1 = lamfeat[2 * k + 1];
-        const double o = lam[k];
-        const double go = gl * o * (1.0 - o);
-        for (int i = 0; i < H; ++i) {
-          const double h = tanh((double)params[pl.lW1 + 2 * i] * x0 + (double)params[pl.lW1 + 2 * i + 1] * x1 + (double)params[pl.lb1 + i]);
-          const double d1 = go * (double)params[pl.lW2 + i] * (1.0 - h * h);
-          const float first = (k == 0) ? 0.f : 1.f;
-          grad_params[pl.lW2 + i] = first * grad_params[pl.lW2 + i] + (float)(go * h);
-          grad_params[pl.lW1 + 2 * i] = first * grad_params[pl.lW1 + 2 * i] + (float)(d1 * x0);
-          grad_params[pl.lW1 + 2 * i + 1] = first * grad_params[pl.lW1 + 2 * i + 1] + (float)(d1 * x1);
-          grad_params[pl.lb1 + i] = first * grad_params[pl.lb1 + i] + (float)d1;
+    // lambda_f: the L layer sums in parallel (a warp per layer, fixed order inside the warp), then the chain through
+    // the 2-H-1 MLP with one thread per (layer, hidden unit), then one thread per output adds the layers up in order --
+    // round 1 walked the layers one after the other with FP64 tanh on a single thread (32 us of a 2.4 ms epoch)
+    __shared__ double s_c[4][UGLAD_MAX_H][32];   // per layer of the current chunk: d(lW2), d(lW1[:,0]), d(lW1[:,1]), d(lb1)
+    __shared__ double s_go[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = EW_THREADS >> 5;
+    double run = 0.0;   // threads 0 .. 4H own one output each: its sum over the layers, in layer order
+    for (int k0 = 0; k0 < L; k0 += 32) {
+      const int kn = min(32, L - k0);
+      for (int kk = warp; kk < kn; kk += nw) {
+        const int k = k0 + kk;
+        double s = 0.0;
+        for (int r = lane; r < nblk; r += 32)
+          s += 4.0 * (double)trh_part[(size_t)k * nblk + r] + (double)sgb_part[(size_t)k * nblk + r];
+        s = warp_sum_d(s);
+        if (lane == 0) {
+          const double l = lam[k];
+          const double gl = -s / (l * l);
+          s_go[kk] = gl * l * (1.0 - l);
         }
-        grad_params[pl.lb2] = ((k == 0) ? 0.f : grad_params[pl.lb2]) + (float)go;
       }
       __syncthreads();
+      for (int t = threadIdx.x; t < kn * H; t += EW_THREADS) {
+        const int kk = t / H, i = t - kk * H, k = k0 + kk;
+        const double x0 = lamfeat[2 * k], x1 = lamfeat[2 * k + 1], go = s_go[kk];
+        const double h = tanh((double)params[pl.lW1 + 2 * i] * x0 + (double)params[pl.lW1 + 2 * i + 1] * x1 + (double)params[pl.lb1 + i]);
+        const double d1 = go * (double)params[pl.lW2 + i] * (1.0 - h * h);
+        s_c[0][i][kk] = go * h;
+        s_c[1][i][kk] = d1 * x0;
+        s_c[2][i][kk] = d1 * x1;
+        s_c[3][i][kk] = d1;
+      }
+      __syncthreads();
+      if ((int)threadIdx.x < 4 * H + 1) {
+        const int o = threadIdx.x;
+        for (int kk = 0; kk < kn; ++kk) run += (o == 4 * H) ? s_go[kk] : s_c[o / H][o % H][kk];
+      }
+      __syncthreads();
+    }
+    if ((int)threadIdx.x < 4 * H + 1) {
+      const int o = threadIdx.x;
+      const float v = (float)run;
+      if (o == 4 * H) grad_params[pl.lb2] = v;
+      else {
+        const int which = o / H, i = o % H;
+        if (which == 0) grad_params[pl.lW2 + i] = v;
+        else if (which == 1) grad_params[pl.lW1 + 2 * i] = v;
+        else if (which == 2) grad_params[pl.lW1 + 2 * i + 1] = v;
+        else grad_params[pl.lb1 + i] = v;
+      }
     }
   }
 }
