@@ -600,31 +600,39 @@ __global__ void __launch_bounds__(MAXT, MINB) eig_jacobi_oe_kernel(EigArgs a, in
   }
   const long long t_tail0 = clock64();
 
-  // ---- column norms (every CTA, all columns), validation, eigenvectors of this CTA's share -----
+  // ---- column norms (every CTA, all columns: the validation sum), eigenvectors of this CTA's share, one pass:
+  // a warp per column, one or two float4 per lane (D % 4 == 0 and D <= 200 on this path), normalised rows stored
+  // with 16-byte accesses
   float wsum_part = 0.f;
+  float* Vb = a.Vt + (size_t)b * D * D;
+  const int nq = D >> 2;
   for (int col = warp; col < D; col += nwarps) {
-    const float* u = F + (size_t)col * ld;
+    const float4* u4 = reinterpret_cast<const float4*>(F + (size_t)col * ld);
+    float4 v[2];
     float s = 0.f;
-    for (int r = lane; r < D; r += 32) s = fmaf(u[r], u[r], s);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int q = lane + 32 * j;
+      v[j] = (q < nq) ? u4[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+      s = fmaf(v[j].x, v[j].x, fmaf(v[j].y, v[j].y, fmaf(v[j].z, v[j].z, fmaf(v[j].w, v[j].w, s))));
+    }
     s = warp_sum(s);
     const float nrm = sqrtf(s);
-    if (lane == 0) {
-      wv[col] = nrm;
-      wsum_part += nrm;
+    const float inv = (nrm > 0.f) ? 1.f / nrm : 0.f;
+    if (nc == 1 || (col % nc) == (int)rank) {
+      float4* o4 = reinterpret_cast<float4*>(Vb + (size_t)col * D);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int q = lane + 32 * j;
+        if (q < nq) o4[q] = make_float4(v[j].x * inv, v[j].y * inv, v[j].z * inv, v[j].w * inv);
+      }
+      if (lane == 0) a.w[(size_t)b * D + col] = nrm - sigma;
     }
+    if (lane == 0) wsum_part += nrm;
   }
-  float wsum = block_sum(wsum_part, red);
-  __syncthreads();
+  const float wsum = block_sum(wsum_part, red);
   const float expect = trace + (float)D * sigma;
   const bool pd = fabsf(wsum - expect) <= 2e-3f * fabsf(expect);
-  float* Vb = a.Vt + (size_t)b * D * D;
-  for (int col = (int)rank + nc * warp; col < D; col += nc * nwarps) {
-    const float* u = F + (size_t)col * ld;
-    const float nrm = wv[col];
-    const float inv = (nrm > 0.f) ? 1.f / nrm : 0.f;
-    for (int r = lane; r < D; r += 32) Vb[(size_t)col * D + r] = u[r] * inv;
-    if (lane == 0) a.w[(size_t)b * D + col] = nrm - sigma;
-  }
   if (a.work != nullptr) {
     if (gl == 0 && rot_count) atomicAdd(&s_rot, rot_count);
     __syncthreads();
