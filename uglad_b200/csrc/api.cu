@@ -470,6 +470,7 @@ static int layer_forward_impl(const uglad_dims* d, int k, const float* S, const 
   a.warmVt = warm_ws ? warm_ws + w.Vt + (size_t)k * w.n2 : nullptr;
   a.warm_w = warm_ws ? warm_ws + w.beta + (size_t)k * w.n1 : nullptr;
   a.D = D; a.shift_mode = 1; a.tail = TAIL_LAYER; a.exact_sqrt = d->exact_sqrt;
+  bool split_done = false;
   if (warm_ws && g_eig_pre && ns_use_tc() && eig_raw() && D % 4 == 0 && D >= 16) {
     // warm solve with its two D^3 products (U0 = G V_prev, Rayleigh quotients) on the tcgen05 GEMM: the Jacobi
     // kernel is left with the sweeps and ONE shared-memory matrix (see eig_prep_kernel)
@@ -488,7 +489,10 @@ static int layer_forward_impl(const uglad_dims* d, int k, const float* S, const 
     if (launch_eig(a, B, st)) return 1;
     g.A_hi = Vk;
     if (launch_tc_gemm(g, B, st)) return 1;   // W = V^T G' into the same buffer
-    if (launch_eig_rq_tail(U0, Vk, sig, ws + w.lam + k, B, D, w.ldp, d->exact_sqrt, a.w, fk, a.sroot, a.snorm, st)) return 1;
+    // Rayleigh quotients + f(beta), and in the same pass V = Vt^T (kept for the backward) and V diag f for the product below
+    if (launch_eig_rq_split(U0, Vk, sig, ws + w.lam + k, B, D, w.ldp, d->exact_sqrt, a.w, fk, a.sroot, a.snorm,
+                            ws + w.VS + (size_t)k * 2 * w.n2p, ws + w.sp, st)) return 1;
+    split_done = true;
   } else if (launch_eig(a, B, st)) {
     return 1;
   }
@@ -497,7 +501,8 @@ static int layer_forward_impl(const uglad_dims* d, int k, const float* S, const 
     float* VSk = ws + w.VS + (size_t)k * 2 * w.n2p;
     float* VF = ws + w.sp;
     if (eig_raw()) {   // plain V (kept for the backward) and V diag f; Vt is read in place when its rows are 16-byte multiples
-      if (launch_eigvec_split(Vk, fk, B, D, w.ldp, w.ldp == D ? nullptr : VtSk, nullptr, VSk, nullptr, VF, nullptr, st)) return 1;
+      if (!split_done &&
+          launch_eigvec_split(Vk, fk, B, D, w.ldp, w.ldp == D ? nullptr : VtSk, nullptr, VSk, nullptr, VF, nullptr, st)) return 1;
       if (tc_mm(VF, nullptr, VSk, nullptr, Xk, nullptr, B, D, w.ldp, st)) return 1;
     } else {
       if (launch_eigvec_split(Vk, fk, B, D, w.ldp, VtSk, VtSk + w.n2p, VSk, VSk + w.n2p, VF, VF + w.n2p, st)) return 1;

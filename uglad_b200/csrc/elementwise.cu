@@ -563,6 +563,112 @@ int launch_eig_rq_tail(const float* W, const float* Vt, const float* sig, const 
   return 0;
 }
 
+// eig_rq_tail_kernel and eigvec_split_kernel in one (plain operands, D % 4 == 0): the graph's eigenvectors are staged
+// ONCE in shared memory (rows padded to D + 1 floats: the transposed read below is conflict-free), serve the Rayleigh
+// quotients against W = V^T G', then leave as V = Vt^T and V diag(f) with coalesced stores -- one launch and one pass
+// over Vt instead of two launches and two passes.  One block per graph; dynamic shared memory D (D + 1) + D floats.
+__global__ void __launch_bounds__(512) eig_rq_split_kernel(const float* __restrict__ W, const float* __restrict__ Vt,
+                                                           const float* __restrict__ sig, const float* __restrict__ lam, int D,
+                                                           int ldp, int exact_sqrt, float* __restrict__ w_out,
+                                                           float* __restrict__ f, float* __restrict__ sroot,
+                                                           float* __restrict__ snorm, float* __restrict__ V,
+                                                           float* __restrict__ VF) {
+  extern __shared__ float sm[];
+  float* T = sm;                          // [D][D + 1]: row k = eigenvector k
+  float* wv = sm + (size_t)D * (D + 1);   // [D] eigenvalues, then f
+  __shared__ double redd[32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int ldt = D + 1, nq = D >> 2;
+  const float sigma = sig[b];
+  const float* Wb = W + (size_t)b * D * ldp;
+  const float4* V4 = reinterpret_cast<const float4*>(Vt + (size_t)b * D * D);
+  for (int idx = tid; idx < D * nq; idx += blockDim.x) {
+    const int k = idx / nq, q = idx - k * nq;
+    const float4 v = V4[idx];
+    float* t = T + (size_t)k * ldt + 4 * q;
+    t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+  }
+  __syncthreads();
+  for (int k = warp; k < D; k += nw) {
+    float num = 0.f, den = 0.f;
+    const float4* W4 = reinterpret_cast<const float4*>(Wb + (size_t)k * ldp);
+    const float* t = T + (size_t)k * ldt;
+    for (int j = lane; j < nq; j += 32) {
+      const float4 w4 = W4[j];
+      const float v0 = t[4 * j], v1 = t[4 * j + 1], v2 = t[4 * j + 2], v3 = t[4 * j + 3];
+      num = fmaf(w4.x, v0, fmaf(w4.y, v1, fmaf(w4.z, v2, fmaf(w4.w, v3, num))));
+      den = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, fmaf(v3, v3, den))));
+    }
+    num = warp_sum(num);
+    den = warp_sum(den);
+    if (lane == 0) {
+      const float ev = ((den > 0.f) ? num / den : 0.f) - sigma;
+      wv[k] = ev;
+      w_out[(size_t)b * D + k] = ev;
+    }
+  }
+  __syncthreads();
+  const double c4 = 4.0 / (double)lam[0];
+  double part = 0.0;
+  for (int i = tid; i < D; i += blockDim.x) {
+    const double be = wv[i];
+    const double mu = be * be + c4;
+    part += mu * mu;
+  }
+  const double nrm = sqrt(block_sum_d(part, redd));
+  double part2 = 0.0;
+  float fi[1] = {0.f};
+  for (int i = tid; i < D; i += blockDim.x) {   // (D <= 232 < blockDim.x: one value per thread)
+    const double be = wv[i];
+    const double mu = be * be + c4;
+    double sv;
+    if (exact_sqrt) {
+      sv = sqrt(mu);
+    } else {
+      double y = mu / nrm, z = 1.0;
+#pragma unroll
+      for (int t = 0; t < UGLAD_NS_ITERS; ++t) {
+        const double Tt = 0.5 * (3.0 - z * y);
+        y = y * Tt;
+        z = Tt * z;
+      }
+      sv = y * sqrt(nrm);
+    }
+    sroot[(size_t)b * D + i] = (float)sv;
+    fi[0] = (float)(0.5 * (sv - be));
+    f[(size_t)b * D + i] = fi[0];
+    part2 += sv * sv;
+  }
+  const double sn = sqrt(block_sum_d(part2, redd));   // (its barriers also order the reads of wv above ...)
+  if (tid == 0) snorm[b] = (float)sn;
+  if (tid < D) wv[tid] = fi[0];                        // ... before f replaces the eigenvalues
+  __syncthreads();
+  float* Vb = V + (size_t)b * D * ldp;
+  float* Fb = VF + (size_t)b * D * ldp;
+  for (int idx = tid; idx < D * D; idx += blockDim.x) {
+    const int i = idx / D, k = idx - i * D;
+    const float v = T[(size_t)k * ldt + i];
+    Vb[(size_t)i * ldp + k] = v;
+    Fb[(size_t)i * ldp + k] = v * wv[k];
+  }
+}
+int launch_eig_rq_split(const float* W, const float* Vt, const float* sig, const float* lam, int B, int D, int ldp,
+                        int exact_sqrt, float* w_out, float* f, float* sroot, float* snorm, float* V, float* VF,
+                        cudaStream_t st) {
+  if (D % 4 != 0 || D > 232) { set_error("eig_rq_split: D %% 4 != 0 or D > 232"); return 1; }
+  const size_t smem = ((size_t)D * (D + 1) + D) * sizeof(float);
+  static bool attr_set[16] = {false};
+  int dev = 0;
+  UGLAD_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16 || !attr_set[dev]) {
+    UGLAD_CUDA(cudaFuncSetAttribute(eig_rq_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    if (dev >= 0 && dev < 16) attr_set[dev] = true;
+  }
+  eig_rq_split_kernel<<<B, 512, smem, st>>>(W, Vt, sig, lam, D, ldp, exact_sqrt, w_out, f, sroot, snorm, V, VF);
+  UGLAD_CHECK_LAUNCH("eig_rq_split_kernel");
+  return 0;
+}
+
 // Eigenvectors for the tcgen05 products: Vt [B][D][D] (row k = eigenvector k) ->
 //   Vt split, V = Vt^T split, and (optionally) VF = V diag(f) split, all [B][D][ldp].
 // 32x32 tiles through shared memory, block (32, 8).
