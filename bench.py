@@ -475,6 +475,8 @@ def time_gpu_workload(name, steps, warmup, rank, world, group, dev, scaling="wea
     units = B_total * L_LAYERS * steps
     del S, loss_S
     ops.reset_warm_start()
+    if gs is not None:
+        gs.close()   # the captured graphs (with the captured gradient all-reduce) go now, not when the collector runs
     del gs
     return dict(cuda_graph=(graph_note or ("replayed" if use_graph else "off")),
                 value=units / ms_total * 1e3, ms_per_step=ms_total / steps, e2e_value=units / ms_e2e * 1e3,
@@ -672,6 +674,16 @@ def main():
         }
         emit(line)
     if world > 1:
+        # The result line is out.  Should the teardown of some rank ever block (a captured collective that outlives the
+        # communicator did exactly that once: 6 minutes until the driver's limit), leave anyway after half a minute.
+        wd = threading.Timer(30.0, lambda: os._exit(0))
+        wd.daemon = True
+        wd.start()
+        # nothing that captured a collective may outlive the communicator: collect, drain, meet, then tear down
+        import gc
+        gc.collect()
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)
         dist.destroy_process_group()
 
 

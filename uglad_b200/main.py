@@ -100,8 +100,10 @@ def _fit_loop(Sb, model, optimizer, EPOCHS, L, INIT_DIAG, VERBOSE, loss_Sb=None,
             print(f"{tag}epoch:{e}/{EPOCHS} loss:{shown.item()}")
         optimizer.step()
         losses.append(shown)
-    if gs is not None and predTheta is not None:
-        predTheta = predTheta.clone()   # the replayed epochs write their theta into static buffers
+    if gs is not None:
+        if predTheta is not None:
+            predTheta = predTheta.clone()   # the replayed epochs write their theta into static buffers
+        gs.close()                          # graphs (and a captured gradient all-reduce) are released here, not by the collector
     return predTheta, losses
 
 

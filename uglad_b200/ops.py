@@ -436,14 +436,18 @@ class GraphedStep:
         params = [p for p in model.parameters()]
         self.params = params
         self.backup = [torch.empty_like(p) for p in params] if nan_guard else None
+        # The epoch closure must not reference `self`: it is stored on the instance, and a reference cycle would keep the
+        # captured graphs (with their captured NCCL all-reduce) alive until the cyclic collector runs -- possibly after
+        # dist.destroy_process_group(), which then waits for them for ever.
+        ws_pair, backup, S_static, loss_static = self.ws, self.backup, self.S, self.loss_S
 
         def epoch(i, warm, guard=False):
-            with use_workspace(self.ws[i], warm):
-                if self.backup is not None:
+            with use_workspace(ws_pair[i], warm):
+                if backup is not None:
                     with torch.no_grad():
-                        torch._foreach_copy_(self.backup, params)
+                        torch._foreach_copy_(backup, params)
                 optimizer.zero_grad(set_to_none=True)
-                theta, loss = ug.forward_uGLAD(self.S, model, L=L, INIT_DIAG=INIT_DIAG, loss_Sb=self.loss_S,
+                theta, loss = ug.forward_uGLAD(S_static, model, L=L, INIT_DIAG=INIT_DIAG, loss_Sb=loss_static,
                                                struct_theta=struct_theta, group=group, total_graphs=total_graphs)
                 if guard and bool(torch.isnan(loss.detach())):
                     return theta.detach(), loss.detach(), True   # no update (main.py:405-409)
@@ -497,6 +501,16 @@ class GraphedStep:
         self.graphs, self.out, self.kernels_per_graph = graphs, out, kpg
         if self.calls >= self.eager_epochs:
             self.calls -= self.eager_epochs   # replays are indexed from graph 0 (= the epoch after four eager ones)
+
+    def close(self):
+        """Drop the captured graphs, their outputs and workspaces NOW (do this before dist.destroy_process_group():
+        a graph that captured the gradient all-reduce keeps the NCCL communicator busy until it is destroyed)."""
+        self.out = []
+        self.graphs = None
+        self._capture_tried = True
+        self._epoch = None
+        self.ws = None
+        self.backup = None
 
     def step_guarded(self, guard=False):
         """One epoch: (theta_pred, loss, stopped).  Eager for the first four calls of a lazy instance, replayed after the
