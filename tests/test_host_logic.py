@@ -24,3 +24,15 @@ def test_bench_tears_down_in_order_behind_a_watchdog():
     tail = src[src.rindex("if world > 1:"):]
     assert tail.index("threading.Timer") < tail.index("gc.collect()") < tail.index("dist.barrier") < tail.index("destroy_process_group")
     assert "gs.close()" in src
+
+
+def test_eig_path_policy():
+    """uglad_eig_path(B, D): the eigensolver path up to small_d_max (166), and up to D = 200 (D % 4 == 0) while every
+    graph's warm solves fit a resident cluster of 4 CTAs (4 B <= 132 on a 148-SM part; without a device the library
+    assumes 148 SMs).  A pure predicate: callable without a GPU."""
+    from uglad_b200 import _lib
+    lib = _lib.load()
+    assert lib.uglad_small_d_max() == 166
+    for B, D, want in [(1, 10, 1), (256, 100, 1), (256, 166, 1), (1, 167, 0), (32, 200, 1), (33, 200, 1), (34, 200, 0),
+                       (256, 200, 0), (4, 198, 0), (4, 204, 0), (1, 1000, 0), (1, 168, 1)]:
+        assert lib.uglad_eig_path(B, D) == want, (B, D)
