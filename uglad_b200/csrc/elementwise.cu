@@ -446,7 +446,7 @@ int launch_phi_split(float* Gh, float* Gl, const float* beta, const float* sroot
 //   GEMM            : U0^T = V_prev^T G'   (row k = G' v_k: the solver's column-major start matrix)
 //   Jacobi kernel   : sweeps on U0 only (EigArgs::pre), eigenvectors out
 //   GEMM            : W = V^T G'
-//   eig_rq_tail_kernel : Rayleigh quotients beta_k = <W_k, v_k> / <v_k, v_k> - sigma, then f(beta) and the
+//   eig_rq_split_kernel: Rayleigh quotients beta_k = <W_k, v_k> / <v_k, v_k> - sigma, then f(beta) and the
 //                     Newton-Schulz scalars of glad.py:140-142 / torch_sqrtm.py:12-28 (the solver's TAIL_LAYER)
 // One block per graph.
 __global__ void __launch_bounds__(256) eig_prep_kernel(const float* __restrict__ S, long long sS,
@@ -495,75 +495,8 @@ int launch_eig_prep(const float* S, long long sS, const float* Theta, const floa
   return 0;
 }
 
-__global__ void __launch_bounds__(512) eig_rq_tail_kernel(const float* __restrict__ W, const float* __restrict__ Vt,
-                                                          const float* __restrict__ sig, const float* __restrict__ lam, int D,
-                                                          int ldp, int exact_sqrt, float* __restrict__ w_out,
-                                                          float* __restrict__ f, float* __restrict__ sroot,
-                                                          float* __restrict__ snorm) {
-  extern __shared__ float wv[];   // [D] eigenvalues
-  __shared__ double redd[32];
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-  const float sigma = sig[b];
-  const float* Wb = W + (size_t)b * D * ldp;
-  const float* Vb = Vt + (size_t)b * D * D;
-  for (int k = warp; k < D; k += nw) {
-    float num = 0.f, den = 0.f;
-    const float4* V4 = reinterpret_cast<const float4*>(Vb + (size_t)k * D);      // D % 4 == 0: 16-byte rows
-    const float4* W4 = reinterpret_cast<const float4*>(Wb + (size_t)k * ldp);
-    for (int j = lane; j < D / 4; j += 32) {
-      const float4 v = V4[j], w4 = W4[j];
-      num = fmaf(w4.x, v.x, fmaf(w4.y, v.y, fmaf(w4.z, v.z, fmaf(w4.w, v.w, num))));
-      den = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, den))));
-    }
-    num = warp_sum(num);
-    den = warp_sum(den);
-    if (lane == 0) {
-      const float ev = ((den > 0.f) ? num / den : 0.f) - sigma;
-      wv[k] = ev;
-      w_out[(size_t)b * D + k] = ev;
-    }
-  }
-  __syncthreads();
-  const double c4 = 4.0 / (double)lam[0];
-  double part = 0.0;
-  for (int i = tid; i < D; i += blockDim.x) {
-    const double be = wv[i];
-    const double mu = be * be + c4;
-    part += mu * mu;
-  }
-  const double nrm = sqrt(block_sum_d(part, redd));
-  double part2 = 0.0;
-  for (int i = tid; i < D; i += blockDim.x) {
-    const double be = wv[i];
-    const double mu = be * be + c4;
-    double sv;
-    if (exact_sqrt) {
-      sv = sqrt(mu);
-    } else {
-      double y = mu / nrm, z = 1.0;
-#pragma unroll
-      for (int t = 0; t < UGLAD_NS_ITERS; ++t) {
-        const double T = 0.5 * (3.0 - z * y);
-        y = y * T;
-        z = T * z;
-      }
-      sv = y * sqrt(nrm);
-    }
-    sroot[(size_t)b * D + i] = (float)sv;
-    f[(size_t)b * D + i] = (float)(0.5 * (sv - be));
-    part2 += sv * sv;
-  }
-  const double sn = sqrt(block_sum_d(part2, redd));
-  if (tid == 0) snorm[b] = (float)sn;
-}
-int launch_eig_rq_tail(const float* W, const float* Vt, const float* sig, const float* lam, int B, int D, int ldp,
-                       int exact_sqrt, float* w_out, float* f, float* sroot, float* snorm, cudaStream_t st) {
-  eig_rq_tail_kernel<<<B, 512, (size_t)D * sizeof(float), st>>>(W, Vt, sig, lam, D, ldp, exact_sqrt, w_out, f, sroot, snorm);
-  UGLAD_CHECK_LAUNCH("eig_rq_tail_kernel");
-  return 0;
-}
-
-// eig_rq_tail_kernel and eigvec_split_kernel in one (plain operands, D % 4 == 0): the graph's eigenvectors are staged
+// The Rayleigh-quotient tail and the eigenvector transpose in one (plain operands, D % 4 == 0; round 2 first had two
+// kernels, eig_rq_tail + eigvec_split): the graph's eigenvectors are staged
 // ONCE in shared memory (rows padded to D + 1 floats: the transposed read below is conflict-free), serve the Rayleigh
 // quotients against W = V^T G', then leave as V = Vt^T and V diag(f) with coalesced stores -- one launch and one pass
 // over Vt instead of two launches and two passes.  One block per graph; dynamic shared memory D (D + 1) + D floats.

@@ -193,8 +193,6 @@ int launch_phi_split(float* Gh, float* Gl, const float* beta, const float* sroot
                      int exact_sqrt, int B, int D, int ldp, float* trh_part, cudaStream_t st);
 int launch_eig_prep(const float* S, long long sS, const float* Theta, const float* lam, const float* warm_w, int B,
                     int D, int ldp, float* G, float* sig, float* tr, cudaStream_t st);
-int launch_eig_rq_tail(const float* W, const float* Vt, const float* sig, const float* lam, int B, int D, int ldp,
-                       int exact_sqrt, float* w_out, float* f, float* sroot, float* snorm, cudaStream_t st);
 // rq_tail + eigvec_split fused (plain operands, D % 4 == 0): also writes V = Vt^T and V diag(f), both [B][D][ldp]
 int launch_eig_rq_split(const float* W, const float* Vt, const float* sig, const float* lam, int B, int D, int ldp,
                         int exact_sqrt, float* w_out, float* f, float* sroot, float* snorm, float* V, float* VF,
