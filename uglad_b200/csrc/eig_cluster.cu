@@ -715,7 +715,9 @@ int eig_cluster_size(int B, int D) {
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   // clusters of 4 strand some SMs (GPC sizes 16 / 18 / 20): leave a margin instead of a second wave
   if (B * 4 <= sms - 16) return 4;
-  if (B * 2 <= sms) return 2;
+  // (clusters of 2 -- 16 lanes per pair to stay within 512 threads -- are available through the knob and tested, but
+  // were not re-measured after the sweep rewrites, where 16-lane groups fell behind: batches of 34 .. 74 graphs take the
+  // one-CTA form, one CTA per SM)
   return 1;
 }
 
